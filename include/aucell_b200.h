@@ -1,0 +1,137 @@
+/*
+ * aucell_b200.h -- C-ABI of the B200-native AUCell hot path (libaucell_b200.so).
+ *
+ * Drop-in boundary for the one data-parallel path of aertslab/pySCENIC this repository replaces:
+ *
+ *     pyscenic.aucell.create_rankings      reference src/pyscenic/aucell.py:25-51
+ *     pyscenic.aucell.derive_auc_threshold reference src/pyscenic/aucell.py:54-72   (per-cell non-zero counts)
+ *     pyscenic.aucell.aucell4r/_enrichment reference src/pyscenic/aucell.py:78-182
+ *     pyscenic.aucell.aucell               reference src/pyscenic/aucell.py:185-213
+ *     ctxcore.recovery.enrichment4cells -> aucs -> auc2d -> weighted_auc1d
+ *                                          (third-party, call sites src/pyscenic/aucell.py:95,122-126)
+ *
+ * The reference is pure Python, so "the reference's FFI for this path" is a ctypes binding; the stub a
+ * maintainer would add to pyscenic/aucell.py is shown in INTEGRATION.md.  Everything here is extern "C" with
+ * plain pointers and sizes.  No torch types.  There is NO CPU fallback: every entry point needs an sm_100
+ * device and fails with AUCELL_ERR_CUDA / AUCELL_ERR_NO_DEVICE otherwise.
+ *
+ * Division of labour.  The HOST (Python, pyscenic_b200/) owns: the seeded column
+ * permutation (numpy legacy RandomState, as pandas' DataFrame.sample draws it), gene-name -> column
+ * resolution, the 80 % rule, noweights, rank_cutoff (Python banker's rounding), max_auc, normalize, and
+ * DataFrame assembly.  THIS LIBRARY owns everything per cell: ranking with the seeded tie order and the
+ * recovery-curve AUC of every regulon.
+ *
+ * Conventions
+ *   - "shuffled position" j of a gene column g: perm[j] == g.  Ties rank in ascending shuffled position, NaN
+ *     last, -0.0 == +0.0 (pandas rank(method="first", ascending=False, na_option="bottom") after the column
+ *     shuffle, aucell.py:46-51).
+ *   - Ranking matrices are uint32, 0-based, laid out [n_cells x n_genes] in SHUFFLED column order (column j
+ *     is gene perm[j]) -- exactly the frame create_rankings returns (aucell.py:47 keeps the shuffled order).
+ *   - AUC matrices are float64 [n_cells x n_regulons], row-major, regulons in the order given to the plan.
+ *   - CSR inputs must be canonical (column indices unique per row); indptr is int64, indices int32.
+ *   - All device entry points are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy
+ *     default stream).  Pointers named d_* are device pointers owned by the caller, h_* host pointers.
+ *   - Return value: 0 on success, a negative AUCELL_ERR_* otherwise; aucell_b200_last_error() gives the
+ *     message of the last failure on the calling thread.
+ */
+#ifndef AUCELL_B200_H
+#define AUCELL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUCELL_B200_ABI_VERSION 1
+
+enum {
+    AUCELL_OK = 0,
+    AUCELL_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, cutoff out of range, ...) */
+    AUCELL_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed                                 */
+    AUCELL_ERR_NO_DEVICE = -3, /* no CUDA device / not an sm_100 device                                */
+    AUCELL_ERR_UNSUPPORTED = -4, /* shape outside what the kernels support (see aucell_b200_limits)   */
+    AUCELL_ERR_NOMEM = -5
+};
+
+/* opaque: per-call constants of one AUCell job, resident on one device */
+typedef struct aucell_plan aucell_plan_t;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int aucell_b200_abi_version(void);
+const char* aucell_b200_last_error(void);
+/* device_count < 0 on failure.  cc = 10*major + minor of `device`; sm_count its SM count. */
+int aucell_b200_device_info(int device, int* device_count, int* cc, int* sm_count, int64_t* smem_optin_bytes);
+/* largest n_genes the shared-memory kernels accept on this build */
+int64_t aucell_b200_max_genes(void);
+
+/* ---- plan: permutation + regulon tables + cutoff (host -> device, once per aucell() call) ------------
+ *
+ * h_perm[n_genes]          perm[j] = gene column at shuffled position j.  NULL = identity (aucell4r path,
+ *                          where the caller already holds a ranking matrix).
+ * n_regulons, h_reg_indptr[n_regulons+1], h_reg_cols[nnz], h_reg_weights[nnz]
+ *                          regulon CSR over gene COLUMN indices of the expression matrix (the columns
+ *                          rnk_mtx.columns.isin(regulon.genes) selects, ctxcore enrichment4cells), fp64 weights
+ *                          (regulon[gene]).  h_reg_weights == NULL means every weight is 1.0 (noweights=True,
+ *                          aucell.py:124,147-148): the kernels then accumulate in exact integers.
+ * h_reg_max_auc[n_regulons] float((rank_cutoff + 1) * weights.sum())  (ctxcore aucs); must be > 0 where valid.
+ * h_reg_valid[n_regulons]  0 = fewer than 80 % of the regulon's genes are in the matrix -> column of zeros.
+ * rank_cutoff              ctxcore derive_rank_cutoff: int(round(auc_threshold * n_genes)) - 1; only ranks
+ *                          strictly below it contribute.  Must satisfy 0 <= rank_cutoff < n_genes.
+ *                          n_regulons == 0 is allowed (ranking-only plan; rank_cutoff ignored).
+ */
+int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32_t n_regulons,
+                       const int64_t* h_reg_indptr, const int32_t* h_reg_cols, const double* h_reg_weights,
+                       const double* h_reg_max_auc, const uint8_t* h_reg_valid, int64_t rank_cutoff,
+                       aucell_plan_t** out_plan);
+int aucell_plan_destroy(aucell_plan_t* plan);
+
+/* ---- create_rankings (aucell.py:25-51): full uint32 ranking rows, shuffled column order --------------
+ * d_out_rank [n_cells x n_genes] uint32.  d_out_nnz (nullable) [n_cells] int32 = np.count_nonzero per cell
+ * (derive_auc_threshold, aucell.py:67: NaN counts as non-zero, -0.0 does not). */
+int aucell_rank_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
+                          uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream);
+int aucell_rank_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
+                          uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream);
+int aucell_rank_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                        const float* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
+                        void* stream);
+int aucell_rank_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                        const double* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
+                        void* stream);
+
+/* ---- aucell (aucell.py:185-213): ranking fused with the AUC of every regulon; the cells x genes ranking
+ * matrix is never written.  d_out_auc [n_cells x n_regulons] float64, d_out_nnz nullable as above. -------- */
+int aucell_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
+                     double* d_out_auc, int32_t* d_out_nnz, void* stream);
+int aucell_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
+                     double* d_out_auc, int32_t* d_out_nnz, void* stream);
+int aucell_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                   const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
+int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                   const double* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
+
+/* ---- aucell4r (aucell.py:98-182): AUCs from an existing uint32 ranking matrix [n_cells x n_genes]
+ * (row_stride in elements).  The plan's regulon columns index the ranking matrix' columns directly (create the
+ * plan with h_perm == NULL). */
+int aucell_from_rankings_u32(const aucell_plan_t* plan, const uint32_t* d_rank, int64_t n_cells,
+                             int64_t row_stride, double* d_out_auc, void* stream);
+
+/* ---- host-buffer entry points: what a CPU caller (the reference's aucell()) binds -----------------------
+ * Inputs and output live in HOST memory (pinned or pageable).  The library streams cell chunks through the
+ * device on its own streams (H2D, kernel, D2H overlapped) and returns when h_out_auc is complete.
+ * chunk_cells <= 0 picks a default.  h_out_nnz nullable. */
+int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, const int32_t* h_indices,
+                        const float* h_data, int64_t n_cells, double* h_out_auc, int32_t* h_out_nnz,
+                        int64_t chunk_cells);
+int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
+                          double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
+
+/* ---- instrumentation -------------------------------------------------------------------------------- */
+/* number of kernels this library has launched on the calling process since load (bench.py gpu_launches) */
+int64_t aucell_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUCELL_B200_H */

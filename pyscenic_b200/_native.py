@@ -1,0 +1,186 @@
+# -*- coding: utf-8 -*-
+"""
+ctypes binding of ``libaucell_b200.so`` (C-ABI declared in ``include/aucell_b200.h``) and its in-tree build.
+
+There is no CPU fallback: if the library cannot be loaded, or no sm_100 device is present, every compute entry
+point raises.  The shared object is built in-tree (``pyscenic_b200/libaucell_b200.so``) with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from typing import List, Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG_DIR)
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+_INCLUDE = os.path.join(_ROOT, "include")
+LIB_NAME = "libaucell_b200.so"
+LIB_PATH = os.path.join(_PKG_DIR, LIB_NAME)
+
+NVCC_FLAGS = [
+    "-O3",
+    "-std=c++17",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler",
+    "-fPIC",
+    "-shared",
+]
+
+# every symbol include/aucell_b200.h declares (tests check that the library exports each of them)
+EXPORTED_SYMBOLS = [
+    "aucell_b200_abi_version",
+    "aucell_b200_last_error",
+    "aucell_b200_device_info",
+    "aucell_b200_max_genes",
+    "aucell_plan_create",
+    "aucell_plan_destroy",
+    "aucell_rank_dense_f32",
+    "aucell_rank_dense_f64",
+    "aucell_rank_csr_f32",
+    "aucell_rank_csr_f64",
+    "aucell_dense_f32",
+    "aucell_dense_f64",
+    "aucell_csr_f32",
+    "aucell_csr_f64",
+    "aucell_from_rankings_u32",
+    "aucell_csr_f32_host",
+    "aucell_dense_f32_host",
+    "aucell_b200_launch_count",
+]
+
+
+class AUCellNativeError(RuntimeError):
+    """A call into libaucell_b200.so failed (the message is the library's own)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__("libaucell_b200: error {}: {}".format(code, message))
+        self.code = code
+
+
+def _sources() -> List[str]:
+    return sorted(
+        os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".h"))
+    ) + [os.path.join(_INCLUDE, "aucell_b200.h")]
+
+
+def _nvcc() -> Optional[str]:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a in-tree.  Cross-compiles without a GPU."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build {} (set NVCC or add nvcc to PATH)".format(LIB_NAME))
+    cmd = (
+        [nvcc]
+        + NVCC_FLAGS
+        + ["-I", _INCLUDE, "-I", _CSRC, "-o", LIB_PATH + ".tmp", os.path.join(_CSRC, "aucell_b200.cu")]
+    )
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n{}\n{}".format(" ".join(cmd), res.stdout))
+    if verbose:
+        print(res.stdout)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load(auto_build: bool = True) -> ctypes.CDLL:
+    """Load the library (building it first when sources are newer and nvcc is available)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if auto_build and is_stale() and _nvcc() is not None:
+            build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "{} is missing and could not be built; pyscenic_b200 has no CPU fallback. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` on a machine with nvcc.".format(LIB_PATH)
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        c_int, i32, i64 = ctypes.c_int, ctypes.c_int32, ctypes.c_int64
+        p = ctypes.c_void_p
+        lib.aucell_b200_abi_version.argtypes = []
+        lib.aucell_b200_abi_version.restype = c_int
+        lib.aucell_b200_last_error.argtypes = []
+        lib.aucell_b200_last_error.restype = ctypes.c_char_p
+        lib.aucell_b200_device_info.argtypes = [c_int, p, p, p, p]
+        lib.aucell_b200_device_info.restype = c_int
+        lib.aucell_b200_max_genes.argtypes = []
+        lib.aucell_b200_max_genes.restype = i64
+        lib.aucell_b200_launch_count.argtypes = []
+        lib.aucell_b200_launch_count.restype = i64
+        lib.aucell_plan_create.argtypes = [c_int, i64, p, i32, p, p, p, p, p, i64, p]
+        lib.aucell_plan_create.restype = c_int
+        lib.aucell_plan_destroy.argtypes = [p]
+        lib.aucell_plan_destroy.restype = c_int
+        for name in ("aucell_rank_dense_f32", "aucell_rank_dense_f64"):
+            f = getattr(lib, name)
+            f.argtypes = [p, p, i64, i64, p, p, p]
+            f.restype = c_int
+        for name in ("aucell_rank_csr_f32", "aucell_rank_csr_f64"):
+            f = getattr(lib, name)
+            f.argtypes = [p, p, p, p, i64, p, p, p]
+            f.restype = c_int
+        for name in ("aucell_dense_f32", "aucell_dense_f64"):
+            f = getattr(lib, name)
+            f.argtypes = [p, p, i64, i64, p, p, p]
+            f.restype = c_int
+        for name in ("aucell_csr_f32", "aucell_csr_f64"):
+            f = getattr(lib, name)
+            f.argtypes = [p, p, p, p, i64, p, p, p]
+            f.restype = c_int
+        lib.aucell_from_rankings_u32.argtypes = [p, p, i64, i64, p, p]
+        lib.aucell_from_rankings_u32.restype = c_int
+        lib.aucell_csr_f32_host.argtypes = [p, p, p, p, i64, p, p, i64]
+        lib.aucell_csr_f32_host.restype = c_int
+        lib.aucell_dense_f32_host.argtypes = [p, p, i64, i64, p, p, i64]
+        lib.aucell_dense_f32_host.restype = c_int
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().aucell_b200_last_error()
+        raise AUCellNativeError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def device_info(device: int = 0):
+    """(device_count, compute_capability, sm_count, smem_optin_bytes) -- raises without a usable device."""
+    lib = load()
+    n, cc, sms = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    smem = ctypes.c_int64(0)
+    check(lib.aucell_b200_device_info(device, ctypes.byref(n), ctypes.byref(cc), ctypes.byref(sms), ctypes.byref(smem)))
+    return n.value, cc.value, sms.value, smem.value
+
+
+def launch_count() -> int:
+    return int(load().aucell_b200_launch_count())
