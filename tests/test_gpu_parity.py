@@ -1,0 +1,376 @@
+# -*- coding: utf-8 -*-
+"""
+GPU parity tests (``-m gpu``): the CUDA path, called through the C-ABI of libaucell_b200.so, against
+  (1) the committed golden vectors produced by executing the reference (tests/golden/make_golden.py),
+  (2) the CPU oracle (oracle/) on seeded inputs,
+  (3) size-independent properties at larger sizes.
+
+Bars (SURVEY.md 8c / BASELINE.json north_star):
+  rankings ............ bit-exact
+  unweighted AUC ...... bit-exact (integer numerator, one IEEE fp64 divide)
+  weighted AUC ........ relative error <= 1e-6 (RTOL below); the kernel sums w*(cutoff-rank) in a fixed tree
+                        order, the reference sums diff(x)*cumsum(w) sequentially -> differences ~1e-16.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import synth
+from oracle import aucell_oracle as O
+from pyscenic_b200.genesig import GeneSignature
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # tolerance stated by BASELINE.json's north_star for floating-point AUCs
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "aucell_golden.npz"))
+
+
+def frame(values, prefix="g"):
+    return pd.DataFrame(values, index=["c%d" % i for i in range(values.shape[0])],
+                        columns=["%s%d" % (prefix, j) for j in range(values.shape[1])])
+
+
+def cuda(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_rank_dense(values, perm):
+    from pyscenic_b200.plan import AUCellPlan
+
+    with AUCellPlan(values.shape[1], perm, None) as plan:
+        return plan.rank_dense(cuda(values)).cpu().numpy().view(np.uint32)
+
+
+def gpu_rank_csr(csr, perm):
+    from pyscenic_b200.plan import AUCellPlan
+
+    with AUCellPlan(csr.shape[1], perm, None) as plan:
+        r = plan.rank_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.int32)), cuda(csr.data))
+        return r.cpu().numpy().view(np.uint32)
+
+
+def assert_auc_close(got, want):
+    assert got.shape == want.shape
+    assert np.array_equal(got == 0.0, want == 0.0)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+    err[want == 0.0] = 0.0
+    assert err.max() <= RTOL, "max relative error %g" % err.max()
+
+
+def oracle_auc(values, perm, reg, cutoff, unweighted=False):
+    names, indptr, genes, weights = reg
+    ranks = O.create_rankings_c(values, perm)
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    cols, ws = [], []
+    for k in range(len(names)):
+        p = inv[genes[indptr[k]:indptr[k + 1]]]
+        o = np.argsort(p, kind="stable")
+        cols.append(p[o])
+        ws.append(np.ones(len(o)) if unweighted else weights[indptr[k]:indptr[k + 1]][o])
+    return O.auc_matrix_from_ranks(ranks, cols, ws, [True] * len(names), cutoff)
+
+
+# =============================================================================================== rankings
+@pytest.mark.parametrize("seed", [0, 42, 123])
+def test_rank_dense_golden_adversarial(seed):
+    A = GOLD["adv_expr"]
+    got = gpu_rank_dense(A, GOLD["adv_perm_seed%d" % seed])
+    assert np.array_equal(got, GOLD["adv_rank_seed%d" % seed])
+    got64 = gpu_rank_dense(A.astype(np.float64), GOLD["adv_perm_seed%d" % seed])
+    assert np.array_equal(got64, GOLD["adv_rank_seed%d" % seed])
+
+
+def test_rank_dense_golden_poisson_and_f64():
+    B = GOLD["pois_expr_u8"].astype(np.float32)
+    assert np.array_equal(gpu_rank_dense(B, GOLD["pois_perm_seed42"]), GOLD["pois_rank_seed42"])
+    C = GOLD["f64_expr"]
+    assert np.array_equal(gpu_rank_dense(C, GOLD["f64_perm_seed5"]), GOLD["f64_rank_seed5"])
+
+
+def test_create_rankings_api_matches_reference_frame():
+    from pyscenic_b200.aucell import create_rankings
+
+    A = GOLD["adv_expr"]
+    df = frame(A)
+    got = create_rankings(df, seed=42)
+    want = O.create_rankings(df, seed=42)
+    assert got.values.dtype == np.uint32
+    assert list(got.columns) == list(want.columns) and list(got.index) == list(want.index)
+    assert np.array_equal(got.values, want.values)
+    # float64 frame whose values are not float32-representable takes the f64 kernels
+    dfc = frame(GOLD["f64_expr"])
+    assert np.array_equal(create_rankings(dfc, seed=5).values, GOLD["f64_rank_seed5"])
+    # reference test (tests/test_aucell.py:31-35): every row is a permutation
+    n = A.shape[1]
+    assert (got.astype(np.int64) + 1).sum(axis=1).unique()[0] == (n * (n + 1)) / 2.0
+
+
+def test_rank_csr_vs_oracle_with_explicit_zeros_negatives_nan():
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(3)
+    n_cells, n_genes = 64, 700
+    dense = synth.dense_counts(rs, n_cells, n_genes, density=0.15)
+    dense[5, :] = 0.0                      # empty row
+    dense[6, rs.choice(n_genes, 40, replace=False)] = -1.5     # negatives
+    dense[7, rs.choice(n_genes, 10, replace=False)] = np.nan
+    dense[8, 3] = np.inf; dense[8, 4] = -np.inf
+    csr = sp.csr_matrix(dense)
+    # add explicit stored zeros (and a -0.0): they must rank exactly like implicit zeros
+    csr = csr.tolil(); csr = csr.tocsr()
+    data = csr.data.copy(); data[::17] = 0.0; data[5::29] = -0.0
+    csr = sp.csr_matrix((data, csr.indices, csr.indptr), shape=csr.shape)
+    dense2 = np.asarray(csr.todense(), dtype=np.float32)
+    perm = np.random.RandomState(11).permutation(n_genes)
+    want = O.create_rankings_c(dense2, perm)
+    assert np.array_equal(gpu_rank_csr(csr, perm), want)
+    assert np.array_equal(gpu_rank_dense(dense2, perm), want)
+    assert np.array_equal(gpu_rank_csr(csr.astype(np.float64), perm), want)
+
+
+def test_rank_large_rows_are_permutations_and_match_oracle_sample():
+    # 27,998 genes (10x mouse shape): smem list overflows for the dense-distinct rows -> global scratch path
+    rs = np.random.RandomState(4)
+    n_cells, n_genes = 24, 27998
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.08)
+    X[0] = rs.randn(n_genes).astype(np.float32)          # all distinct, mixed sign: 27,998 explicit entries
+    X[1] = np.abs(rs.randn(n_genes)).astype(np.float32)  # all positive distinct
+    perm = np.random.RandomState(42).permutation(n_genes)
+    got = gpu_rank_dense(X, perm)
+    assert np.array_equal(np.sort(got, axis=1), np.tile(np.arange(n_genes, dtype=np.uint32), (n_cells, 1)))
+    assert np.array_equal(got, O.create_rankings_c(X, perm))
+
+
+def test_rank_more_than_65535_genes_uses_32bit_positions():
+    rs = np.random.RandomState(6)
+    n_cells, n_genes = 6, 70001
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.03)
+    perm = np.random.RandomState(1).permutation(n_genes)
+    assert np.array_equal(gpu_rank_dense(X, perm), O.create_rankings_c(X, perm))
+
+
+# =============================================================================================== fused AUC
+def _cfg1():
+    D = GOLD["cfg1_expr_u8"].astype(np.float32)
+    ip, gg = GOLD["cfg1_sig_indptr"], GOLD["cfg1_sig_genes"]
+    sigs = [GeneSignature(name="sig%02d" % k, gene2weight=["g%d" % g for g in gg[ip[k]:ip[k + 1]]])
+            for k in range(len(ip) - 1)]
+    return frame(D), sigs
+
+
+def test_aucell_cfg1_golden_bit_exact():
+    """BASELINE.json configs[0]: 1,000 x 2,000, 50 unweighted regulons, auc_threshold 0.05, seed 42."""
+    from pyscenic_b200.aucell import aucell
+
+    df, sigs = _cfg1()
+    got = aucell(df, sigs, auc_threshold=0.05, seed=42, num_workers=4)
+    assert got.index.name == "Cell" and got.columns.name == "Regulon"
+    assert list(got.index) == list(df.index) and list(got.columns) == [s.name for s in sigs]
+    assert got.values.dtype == np.float64
+    assert np.array_equal(got.values, GOLD["cfg1_auc"])
+    # serial-branch ordering of the reference: both axes sorted by label
+    got1 = aucell(df, sigs, auc_threshold=0.05, seed=42, num_workers=1)
+    assert list(got1.index) == list(GOLD["cfg1_w1_index"]) and list(got1.columns) == list(GOLD["cfg1_w1_columns"])
+    assert np.array_equal(got1[got.columns].loc[got.index].values, GOLD["cfg1_auc"])
+    gotn = aucell(df, sigs, auc_threshold=0.05, seed=42, normalize=True)
+    assert np.array_equal(gotn.values, GOLD["cfg1_auc_norm"])
+    # float64 frame (what pd.read_csv yields) gives the same result
+    got64 = aucell(df.astype(np.float64), sigs, auc_threshold=0.05, seed=42)
+    assert np.array_equal(got64.values, GOLD["cfg1_auc"])
+
+
+def _weighted_sigs():
+    ip, gg, ww = GOLD["w_sig_indptr"], GOLD["w_sig_genes"], GOLD["w_sig_weights"]
+    names, nfake = GOLD["w_sig_names"], GOLD["w_sig_nfake"]
+    rs = np.random.RandomState(99)
+    sigs = []
+    for k in range(len(names)):
+        g = ["g%d" % x for x in gg[ip[k]:ip[k + 1]]] + ["FAKE%d_%d" % (k, i) for i in range(nfake[k])]
+        w = np.concatenate([ww[ip[k]:ip[k + 1]], rs.lognormal(0, 1, size=nfake[k])])
+        sigs.append(GeneSignature(name=str(names[k]), gene2weight=dict(zip(g, w))))
+    return sigs
+
+
+def test_aucell_weighted_golden(caplog):
+    from pyscenic_b200.aucell import aucell, aucell4r
+
+    E = GOLD["w_expr"]
+    df = frame(E)
+    sigs = _weighted_sigs()
+    with caplog.at_level("WARNING"):
+        got = aucell(df, sigs, auc_threshold=0.05, seed=11)
+    assert "Less than 80% of the genes in TF3(-) are present in the expression matrix." in caplog.text
+    assert (got["TF3(-)"] == 0.0).all()              # < 80 % overlap -> zeros
+    assert (got["TF7(-)"] != 0.0).any()              # exactly 80 % passes
+    assert_auc_close(got.values, GOLD["w_auc"])
+    got_nw = aucell(df, sigs, auc_threshold=0.05, noweights=True, seed=11)
+    assert np.array_equal(got_nw.values, GOLD["w_auc_noweights"])      # integer path: bit-exact
+    # aucell4r from the reference's ranking frame (columns in shuffled order), threshold 0.10
+    perm = GOLD["w_perm_seed11"]
+    rnk = pd.DataFrame(GOLD["w_rank_seed11"], index=df.index, columns=df.columns[perm])
+    got4r = aucell4r(rnk, sigs, auc_threshold=0.10)
+    assert_auc_close(got4r.values, GOLD["w_auc4r_thr10"])
+
+
+def _plan_for(n_genes, perm, reg, cutoff, unweighted=False):
+    from pyscenic_b200.plan import AUCellPlan
+
+    tables = synth.regulon_tables_from_arrays(*reg, n_genes=n_genes, rank_cutoff=cutoff, unweighted=unweighted)
+    return AUCellPlan(n_genes, perm, tables)
+
+
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted):
+    """Cells with fewer positive genes than the cutoff (zeros and even negatives fall below it), n_pos == cutoff,
+    all-zero, NaN/inf cells; dense and CSR variants must agree bit-for-bit with each other."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(21)
+    n_cells, n_genes = 96, 1500
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)      # 74
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.12)
+    X[0] = 0.0
+    X[1] = 0.0; X[1, rs.choice(n_genes, 10, replace=False)] = 2.0          # n_pos = 10 < cutoff
+    X[2] = 0.0; X[2, rs.choice(n_genes, cutoff, replace=False)] = rs.rand(cutoff) + 1   # n_pos == cutoff
+    X[3] = 0.0; X[3, rs.choice(n_genes, cutoff + 1, replace=False)] = 1.0
+    X[4] = -1.0; X[4, rs.choice(n_genes, 20, replace=False)] = 0.0        # 20 zeros on top, negatives below
+    X[5] = -np.abs(rs.randn(n_genes)); X[5, :30] = 3.0                     # 30 pos, no zeros, negatives reach
+    X[6, rs.choice(n_genes, 300, replace=False)] = np.nan
+    X[7] = rs.randn(n_genes)                                               # fully dense, distinct
+    X[8, 0] = np.inf; X[8, 1] = -np.inf
+    X[9] = 5.0                                                             # all equal positive
+    reg = synth.make_regulons(rs, n_genes, 40, 5, 300, weighted=True)
+    perm = np.random.RandomState(7).permutation(n_genes)
+    want = oracle_auc(X, perm, reg, cutoff, unweighted)
+    csr = sp.csr_matrix(X)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted) as plan:
+        import torch
+
+        nnz_d = torch.empty(n_cells, dtype=torch.int32, device="cuda")
+        got_d = plan.aucell_dense(cuda(X), out_nnz=nnz_d).cpu().numpy()
+        got_s = plan.aucell_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.int32)),
+                                cuda(csr.data)).cpu().numpy()
+        got_h = plan.aucell_dense_host(X, chunk_cells=17)
+        got_hs = plan.aucell_csr_host(csr.indptr, csr.indices, csr.data, chunk_cells=13)
+        got_d64 = plan.aucell_dense(cuda(X.astype(np.float64))).cpu().numpy()
+    assert np.array_equal(got_d, got_s) and np.array_equal(got_d, got_h) and np.array_equal(got_d, got_hs)
+    assert np.array_equal(got_d, got_d64)
+    if unweighted:
+        assert np.array_equal(got_d, want)
+    else:
+        assert_auc_close(got_d, want)
+    # np.count_nonzero semantics (derive_auc_threshold): NaN counts, -0.0 does not
+    assert np.array_equal(nnz_d.cpu().numpy(), np.count_nonzero(X, axis=1))
+
+
+def test_fused_csr_config3_shape_vs_oracle():
+    """BASELINE.json configs[2] shape at oracle-friendly scale: 25k genes CSR ~7 % nnz, 500 regulons incl.
+    repressor (-) regulons, weighted; per-cell nnz log-normal so some cells sit below the cutoff of 1,249."""
+    n_cells, n_genes = 256, 25000
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1750, seed=5, device="cuda", sigma=0.6)
+    rs = np.random.RandomState(8)
+    reg = synth.make_regulons(rs, n_genes, 500, 10, 400, weighted=True, repressors=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    assert cutoff == 1249
+    perm = np.random.RandomState(42).permutation(n_genes)
+    ip, ix, dv = indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy()
+    assert (np.diff(ip) < cutoff).any() and (np.diff(ip) > cutoff).any()
+    X = synth.csr_to_dense(ip, ix, dv, n_genes)
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+        got2 = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+    assert_auc_close(got, want)
+    assert np.array_equal(got, got2)      # deterministic
+    want_u = oracle_auc(X, perm, reg, cutoff, unweighted=True)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted=True) as plan:
+        got_u = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+    assert np.array_equal(got_u, want_u)
+
+
+def test_fused_dense_config2_shape_vs_oracle():
+    """BASELINE.json configs[1] shape at oracle-friendly scale: 20k genes dense f32, 300 weighted regulons."""
+    rs = np.random.RandomState(12)
+    n_cells, n_genes = 128, 20000
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.10)
+    reg = synth.make_regulons(rs, n_genes, 300, 10, 1000, weighted=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    assert cutoff == 999
+    perm = np.random.RandomState(42).permutation(n_genes)
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_dense(cuda(X)).cpu().numpy()
+    assert_auc_close(got, want)
+
+
+@pytest.mark.parametrize("thr", [0.01, 0.2, 0.6])
+def test_threshold_sweep_vs_oracle(thr):
+    """BASELINE.json configs[4]: cutoff-bound and gather-bound regimes (incl. a cutoff far above nnz)."""
+    rs = np.random.RandomState(31)
+    n_cells, n_genes = 48, 5000
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.07)
+    reg = synth.make_regulons(rs, n_genes, 60, 10, 600, weighted=True)
+    cutoff = O.derive_rank_cutoff(thr, n_genes)
+    perm = np.random.RandomState(3).permutation(n_genes)
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_dense(cuda(X)).cpu().numpy()
+    assert_auc_close(got, want)
+
+
+def test_sharding_invariance_and_value_range():
+    """Output is independent of how cells are split (what the multi-GPU driver relies on), 0 <= AUC < 1."""
+    n_cells, n_genes = 2000, 27998
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1960, seed=9, device="cuda")
+    rs = np.random.RandomState(2)
+    reg = synth.make_regulons(rs, n_genes, 500, 10, 400, weighted=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(0).permutation(n_genes)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        whole = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+        parts = []
+        for (c0, c1) in [(0, 700), (700, 701), (701, 2000)]:
+            e0 = int(indptr[c0])
+            ip = (indptr[c0:c1 + 1] - e0).contiguous()
+            e1 = int(indptr[c1])
+            parts.append(plan.aucell_csr(ip, indices[e0:e1].contiguous(), data[e0:e1].contiguous()).cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert whole.min() >= 0.0 and whole.max() < 1.0 and np.isfinite(whole).all()
+
+
+def test_sparse_api_equals_dense_api_and_mismatch_behaviour(caplog):
+    import scipy.sparse as sp
+
+    from pyscenic_b200.aucell import aucell
+
+    df, sigs = _cfg1()
+    df = df.iloc[:100]
+    fake = GeneSignature(name="test", gene2weight=list(map("FAKE{}".format, range(100))))
+    with caplog.at_level("WARNING"):
+        d = aucell(df, [fake] + sigs[:10], seed=3)           # reference tests/test_aucell.py:48-54
+    assert "Less than 80% of the genes in test are present" in caplog.text
+    assert (d["test"] == 0.0).all()
+    s = aucell(sp.csr_matrix(df.values), [fake] + sigs[:10], seed=3, genes=list(df.columns), cells=list(df.index))
+    assert np.array_equal(d.values, s.values) and list(d.index) == list(s.index)
+    want = O.aucell(df, [fake] + sigs[:10], seed=3, num_workers=2)
+    assert np.array_equal(d.values, want.values)
+    with pytest.raises(AssertionError):
+        aucell(df, sigs[:2], auc_threshold=1.5, seed=3)
+    with pytest.raises(ValueError):
+        aucell(df, [], seed=3)
+
+
+def test_enrichment_alias_matches_oracle():
+    from pyscenic_b200.aucell import enrichment
+
+    df, sigs = _cfg1()
+    rnk = O.create_rankings(df.iloc[:64], seed=5)
+    got = enrichment(rnk, sigs[0], auc_threshold=0.05)
+    want = O.enrichment4cells(rnk, sigs[0], auc_threshold=0.05)
+    assert list(got.index.names) == ["Cell", "Regulon"] and list(got.columns) == ["AUC"]
+    assert got.index.equals(want.index)
+    assert np.array_equal(got["AUC"].values, want["AUC"].values)

@@ -1,0 +1,182 @@
+# -*- coding: utf-8 -*-
+"""CPU tests of the host side: signature records, regulon resolution (isin / 80 % rule / weights / max_auc),
+the seeded permutation, the rank cutoff, and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import aucell_oracle as O
+from pyscenic_b200 import _native
+from pyscenic_b200.genesig import GeneSignature, Regulon
+from pyscenic_b200.plan import derive_rank_cutoff, permutation_from_seed, prepare_regulons
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GMT = "/root/reference/src/resources/tests/c6.all.v6.1.symbols.gmt"
+
+
+# ------------------------------------------------------------------------------------------ C-ABI library
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "aucell_b200.h")).read()
+    declared = set(re.findall(r"\b(aucell_[a-z0-9_]+)\s*\(", header))
+    declared -= {"aucell_plan_t"}
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.aucell_b200_abi_version() == 1
+    assert lib.aucell_b200_launch_count() >= 0
+
+
+def test_library_has_sm100a_code_only():
+    import subprocess, shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _native.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pyscenic_b200.aucell import aucell
+
+    df = pd.DataFrame(np.eye(4, 30, dtype=np.float32), columns=["g%d" % i for i in range(30)])
+    sig = GeneSignature("s", ["g0", "g1", "g2"])
+    with pytest.raises(_native.AUCellNativeError):
+        aucell(df, [sig], seed=1)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under pyscenic_b200/ may import, load or mention it."""
+    pkg = os.path.join(ROOT, "pyscenic_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), "%s mentions the oracle" % f
+
+
+# ------------------------------------------------------------------------------------------ host arithmetic
+def test_rank_cutoff_equals_oracle():
+    for n in (100, 2000, 2010, 2030, 20000, 25000, 27998, 70001):
+        for thr in (0.01, 0.02, 0.05, 0.1, 0.2, 0.5):
+            assert derive_rank_cutoff(thr, n) == O.derive_rank_cutoff(thr, n)
+    for bad in (0.0, 1.0001, -1):
+        with pytest.raises(AssertionError):
+            derive_rank_cutoff(bad, 100)
+
+
+def test_permutation_is_what_pandas_sample_draws():
+    for seed in (0, 42, 2**31 - 1):
+        n = 257
+        df = pd.DataFrame(np.zeros((1, n)), columns=np.arange(n))
+        want = df.sample(frac=1.0, replace=False, axis=1, random_state=seed).columns.values
+        assert np.array_equal(permutation_from_seed(n, seed), want)
+    # RandomState objects pass through (and advance), None uses the global numpy state
+    rs1, rs2 = np.random.RandomState(5), np.random.RandomState(5)
+    df = pd.DataFrame(np.zeros((1, 50)), columns=np.arange(50))
+    assert np.array_equal(permutation_from_seed(50, rs1), df.sample(frac=1.0, axis=1, random_state=rs2).columns.values)
+    np.random.seed(77)
+    a = permutation_from_seed(50, None)
+    np.random.seed(77)
+    b = df.sample(frac=1.0, axis=1, random_state=None).columns.values
+    assert np.array_equal(a, b)
+
+
+def test_prepare_regulons_matches_reference_membership_rules(caplog):
+    genes = ["g%d" % i for i in range(20)] + ["g3"]          # duplicated column name: both columns selected
+    perm = np.random.RandomState(1).permutation(len(genes))
+    sigs = [
+        GeneSignature("full", {"g0": 2.0, "g1": 0.5, "g3": 1.5}),
+        GeneSignature("eighty", {"g0": 1.0, "g1": 1.0, "g2": 1.0, "g4": 1.0, "zz": 1.0}),      # 4/5 = 0.8 passes
+        GeneSignature("below", {"g0": 1.0, "g1": 1.0, "g2": 1.0, "zz": 1.0, "yy": 1.0}),       # 3/5 < 0.8
+        GeneSignature("none", ["qq", "rr"]),
+    ]
+    with caplog.at_level("WARNING"):
+        t = prepare_regulons(genes, perm, sigs, 0.25, noweights=False)
+    assert t.valid.tolist() == [1, 1, 0, 0]
+    assert "Less than 80% of the genes in below are present in the expression matrix." in caplog.text
+    assert "Less than 80% of the genes in none are present in the expression matrix." in caplog.text
+    assert t.rank_cutoff == O.derive_rank_cutoff(0.25, 21)
+    # "full": g0, g1 and BOTH g3 columns, in shuffled column order
+    cols = t.cols[t.indptr[0]:t.indptr[1]]
+    assert sorted(np.asarray(genes)[cols]) == ["g0", "g1", "g3", "g3"]
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    assert np.all(np.diff(inv[cols]) > 0)
+    w = t.weights[t.indptr[0]:t.indptr[1]]
+    assert np.array_equal(w, [sigs[0][genes[c]] for c in cols])
+    assert t.max_auc[0] == float((t.rank_cutoff + 1) * w.sum())
+    # same answer as the oracle's frame-level enrichment4cells on a real ranking
+    x = np.random.RandomState(2).poisson(1.0, size=(7, len(genes))).astype(np.float32)
+    df = pd.DataFrame(x, columns=genes)
+    rnk = O.create_rankings(df, seed=1)
+    for k, s in enumerate(sigs):
+        e = O.enrichment4cells(rnk, s, 0.25)["AUC"].values
+        if not t.valid[k]:
+            assert (e == 0).all()
+    # noweights -> integer path (weights None)
+    t2 = prepare_regulons(genes, perm, sigs, 0.25, noweights=True)
+    assert t2.weights is None and t2.max_auc[0] == float((t2.rank_cutoff + 1) * 4)
+
+
+def test_all_invalid_signatures_do_not_assert_on_threshold():
+    # the reference only evaluates the cutoff inside aucs(), i.e. for regulons that pass the 80 % rule
+    t = prepare_regulons(["a", "b", "c"], None, [GeneSignature("x", ["q"])], 5.0)
+    assert t.valid.tolist() == [0]
+    with pytest.raises(AssertionError):
+        prepare_regulons(["a", "b", "c"], None, [GeneSignature("x", ["a"])], 5.0)
+
+
+# ------------------------------------------------------------------------------------------ signatures
+def test_gene_signature_record():
+    s = GeneSignature("s", ["a", "b", "c"])
+    assert len(s) == 3 and s["a"] == 1.0 and "b" in s and set(s.genes) == {"a", "b", "c"}
+    w = GeneSignature("w", {"a": 0.1, "b": 3.0, "c": 2.0})
+    assert w.genes == ("b", "c", "a") and w.weights == (3.0, 2.0, 0.1)
+    assert w.noweights().weights == (1.0, 1.0, 1.0) and w.noweights().name == "w"
+    assert GeneSignature("p", [("a", 2.0), ("b", 1.0)])["a"] == 2.0
+    u = w.union(GeneSignature("v", {"a": 5.0, "d": 1.0}))
+    assert u["a"] == 5.0 and len(u) == 4
+    assert w.rename("z").name == "z" and w.add("q", 9.0)["q"] == 9.0
+    assert len(w.difference(s)) == 0 and len(w.intersection(s)) == 3
+    with pytest.raises(AttributeError):
+        w.name = "other"
+    with pytest.raises(ValueError):
+        GeneSignature("", ["a"])
+    assert hash(s) == hash(GeneSignature("s", ["a", "b", "c"])) and s == GeneSignature("s", ["c", "b", "a"])
+
+
+def test_regulon_record():
+    r = Regulon("TF1(+)", {"a": 1.0, "b": 2.0}, transcription_factor="TF1", context=frozenset(["activating"]))
+    assert r.transcription_factor == "TF1" and "activating" in r.context
+    assert isinstance(r.noweights(), Regulon) and r.noweights()["b"] == 1.0
+    r2 = r.union(Regulon("TF1(+)", {"b": 5.0, "c": 1.0}, transcription_factor="TF1", score=3.0))
+    assert r2["b"] == 5.0 and r2.score == 3.0 and len(r2) == 3
+    with pytest.raises(ValueError):
+        Regulon("x", ["a"], transcription_factor="")
+
+
+def test_gmt_round_trip(tmp_path):
+    sigs = [GeneSignature("A", ["g1", "g2", "g3"]), GeneSignature("B", ["g2"])]
+    p = str(tmp_path / "x.gmt")
+    GeneSignature.to_gmt(p, sigs, field_separator="\t", gene_separator="\t")
+    back = GeneSignature.from_gmt(p, field_separator="\t", gene_separator="\t")
+    assert [s.name for s in back] == ["A", "B"] and set(back[0].genes) == {"g1", "g2", "g3"}
+
+
+@pytest.mark.skipif(not os.path.exists(GMT), reason="reference fixture only exists in the build container")
+def test_reference_gmt_fixture_loads():
+    # the signature fixture the reference's own tests use (tests/test_aucell.py:14,22-28)
+    gs = GeneSignature.from_gmt(GMT, gene_separator="\t", field_separator="\t")
+    assert len(gs) == 189
+    assert min(len(s) for s in gs) == 10 and max(len(s) for s in gs) == 481
+    assert sum(len(s) for s in gs) == 31319
