@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "cell_kernels.cuh"
+#include "fused_kernel.cuh"
 
 using namespace aucell;
 
@@ -73,13 +75,17 @@ struct aucell_plan {
     bool weighted = false;
     int n_regulons = 0;
     int64_t reg_nnz = 0;
+    bool acc64 = false;       // 64-bit accumulators (weighted, or cutoff too large for exact u32 sums)
+    int n_acc = 0;
     // device arrays
     int32_t* d_inv_perm = nullptr;
-    int32_t* d_reg_indptr = nullptr;
-    void* d_reg_pos = nullptr;
-    double* d_reg_weight = nullptr;
+    uint32_t* d_tptr = nullptr;
+    unsigned long long* d_tent = nullptr;   // weighted: (W << 16) | accumulator
+    uint16_t* d_tacc16 = nullptr;           // unweighted: accumulator
+    int32_t* d_acc_first = nullptr;
+    uint8_t* d_acc_parts = nullptr;
+    double* d_acc_scale = nullptr;
     double* d_reg_max_auc = nullptr;
-    uint8_t* d_reg_valid = nullptr;
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;
     mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
@@ -87,64 +93,53 @@ struct aucell_plan {
 
 namespace {
 
-RegulonsDev reg_of(const aucell_plan* p) {
-    RegulonsDev r;
+GeneTableDev tab_of(const aucell_plan* p) {
+    GeneTableDev r;
     r.n_regulons = p->n_regulons;
-    r.indptr = p->d_reg_indptr;
-    r.pos = p->d_reg_pos;
-    r.weight = p->d_reg_weight;
+    r.n_acc = p->n_acc;
+    r.tptr = p->d_tptr;
+    r.tent = p->d_tent;
+    r.tacc16 = p->d_tacc16;
+    r.acc_first = p->d_acc_first;
+    r.acc_parts = p->d_acc_parts;
+    r.acc_scale = p->d_acc_scale;
     r.max_auc = p->d_reg_max_auc;
-    r.valid = p->d_reg_valid;
     return r;
 }
 
-// Order the entries of one regulon so that consecutive groups of 32 (one warp load of the gather) touch
-// distinct shared-memory banks of the per-cell table where possible: round-robin over banks.
-void stagger_banks(std::vector<std::pair<int32_t, double>>& ent, bool pos16) {
-    const int shift = pos16 ? 1 : 0;  // two uint16 table entries per 4-byte bank word
-    std::vector<std::vector<std::pair<int32_t, double>>> bank(32);
-    for (auto& e : ent) bank[(e.first >> shift) & 31].push_back(e);
-    for (auto& b : bank) std::sort(b.begin(), b.end());
-    size_t out = 0, level = 0;
-    while (out < ent.size()) {
-        for (int b = 0; b < 32; ++b)
-            if (level < bank[b].size()) ent[out++] = bank[b][level];
-        ++level;
-    }
-}
-
-struct SmemLayout {
-    int cap = 0;
-    int off_key = 0, off_pos = 0, off_bits = 0, off_wpre = 0, off_tbl = 0;
-    int total = 0;
-    int ctas_per_sm = 1;
-};
-
 int align16(int v) { return (v + 15) & ~15; }
 
-// Pick the smem list capacity and the number of resident CTAs per SM.
-bool plan_smem(const aucell_plan* p, int key_bytes, bool fused, SmemLayout* L) {
+// ---- create_rankings kernels --------------------------------------------------------------------------------
+struct RankLayout {
+    int cap = 0, off_key = 0, off_pos = 0, off_bits = 0, off_wpre = 0, total = 0, ctas_per_sm = 1;
+};
+
+int layout_rank(const aucell_plan* p, int key_bytes, int cap, RankLayout* L) {
     const int pos_bytes = p->pos16 ? 2 : 4;
-    const int fixed = align16(p->n_words * 4) * 2 + (fused ? align16(p->n_genes * pos_bytes) : 0);
-    const int per_entry = key_bytes + pos_bytes;
+    int off = 0;
+    L->cap = cap;
+    L->off_key = off; off = align16(off + cap * key_bytes);
+    L->off_pos = off; off = align16(off + cap * pos_bytes);
+    L->off_bits = off; off = align16(off + p->n_words * 4);
+    L->off_wpre = off; off = align16(off + p->n_words * 4);
+    L->total = off;
+    return off;
+}
+
+bool plan_rank_smem(const aucell_plan* p, int key_bytes, RankLayout* L) {
     const int want = std::min(next_pow2(p->n_genes), 4096);
     const int64_t sm_total = 228 * 1024;  // per SM, 1 KB reserved per resident CTA
-    for (int k = 4; k >= 1; --k) {
-        int64_t budget = std::min<int64_t>(p->smem_optin, sm_total / k - 1024);
-        int64_t room = budget - fixed - 64;
-        if (room < (int64_t)per_entry * 2) continue;
-        int cap = 2;
-        while ((int64_t)cap * 2 * per_entry <= room && cap * 2 <= next_pow2(p->n_genes)) cap <<= 1;
-        if (cap < want && k > 1) continue;
-        L->cap = cap;
+    for (int k = 6; k >= 1; --k) {
+        const int64_t budget = std::min<int64_t>(p->smem_optin, sm_total / k - 1024);
+        int cap = 0;
+        for (int c = 2; c <= next_pow2(p->n_genes) && c <= 32768; c <<= 1) {
+            RankLayout t;
+            if (layout_rank(p, key_bytes, c, &t) <= budget) cap = c;
+        }
+        if (cap == 0 || (cap < want && k > 1)) continue;
+        cap = std::min(cap, std::max(want, 8192));
+        layout_rank(p, key_bytes, cap, L);
         L->ctas_per_sm = k;
-        int off = 0;
-        L->off_key = off; off = align16(off + cap * key_bytes);
-        L->off_pos = off; off = align16(off + cap * pos_bytes);
-        L->off_bits = off; off = align16(off + p->n_words * 4);
-        L->off_wpre = off; off = align16(off + p->n_words * 4);
-        L->off_tbl = off; off = align16(off + (fused ? p->n_genes * pos_bytes : 0));
-        L->total = off;
         return true;
     }
     return false;
@@ -169,14 +164,45 @@ int get_scratch(const aucell_plan* p, cudaStream_t st, int key_bytes, int grid, 
     return AUCELL_OK;
 }
 
-template <typename ValT, typename PosT, int IN, int OUT>
-int launch_cell(const aucell_plan* p, CellArgs<ValT>& a, const SmemLayout& L, int grid, cudaStream_t st) {
-    if (OUT == OUT_AUC && p->weighted) {
-        auto k = aucell_cell_kernel<ValT, PosT, IN, OUT, true>;
+template <typename ValT, int IN>
+int run_rank(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
+             const int32_t* indices, const ValT* data, int64_t n_cells, uint32_t* out_rank, int32_t* out_nnz,
+             void* stream) {
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (n_cells == 0) return AUCELL_OK;
+    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
+        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
+    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (!out_rank) return fail(AUCELL_ERR_INVALID, "out_rank is NULL");
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    RankLayout L;
+    const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
+    if (!plan_rank_smem(p, key_bytes, &L))
+        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
+    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * L.ctas_per_sm);
+    CellArgs<ValT> a;
+    memset(&a, 0, sizeof a);
+    a.dense = dense; a.row_stride = row_stride;
+    a.indptr = indptr; a.indices = indices; a.data = data;
+    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
+    a.inv_perm = p->d_inv_perm;
+    a.out_rank = out_rank; a.out_nnz = out_nnz;
+    a.cap = L.cap;
+    a.off_key = L.off_key; a.off_pos = L.off_pos; a.off_bits = L.off_bits; a.off_wpre = L.off_wpre;
+    a.scratch_cap = next_pow2(p->n_genes);
+    if (L.cap < a.scratch_cap) {
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
+        if (rc) return rc;
+    }
+    if (p->pos16) {
+        auto k = aucell_rank_kernel<ValT, uint16_t, IN>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         k<<<grid, kBlock, L.total, st>>>(a);
     } else {
-        auto k = aucell_cell_kernel<ValT, PosT, IN, OUT, false>;
+        auto k = aucell_rank_kernel<ValT, uint32_t, IN>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         k<<<grid, kBlock, L.total, st>>>(a);
     }
@@ -185,51 +211,71 @@ int launch_cell(const aucell_plan* p, CellArgs<ValT>& a, const SmemLayout& L, in
     return AUCELL_OK;
 }
 
-template <typename ValT, int IN, int OUT>
-int run_cells(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
-              const int32_t* indices, const ValT* data, int64_t n_cells, uint32_t* out_rank, double* out_auc,
-              int32_t* out_nnz, void* stream) {
+// ---- fused AUCell kernel ------------------------------------------------------------------------------------
+template <typename ValT, typename PosT, int IN>
+int launch_fused(const aucell_plan* p, const FusedArgs<ValT>& a, int smem, int grid, cudaStream_t st) {
+    if (p->acc64) {
+        auto k = aucell_fused_kernel<ValT, PosT, IN, true>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, kF, smem, st>>>(a);
+    } else {
+        auto k = aucell_fused_kernel<ValT, PosT, IN, false>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, kF, smem, st>>>(a);
+    }
+    g_launches.fetch_add(1);
+    CK(cudaGetLastError());
+    return AUCELL_OK;
+}
+
+template <typename ValT, int IN>
+int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
+              const int32_t* indices, const ValT* data, int64_t n_cells, double* out_auc, int32_t* out_nnz,
+              void* stream) {
     if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
     if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
-    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
-        if (n_cells > 0) return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
-    if (IN == IN_CSR && n_cells > 0 && (!indptr || (!indices && !data)))
-        return fail(AUCELL_ERR_INVALID, "CSR input: NULL pointer");
-    if (OUT == OUT_RANK && !out_rank && n_cells > 0) return fail(AUCELL_ERR_INVALID, "out_rank is NULL");
-    if (OUT == OUT_AUC) {
-        if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
-        if (!out_auc && n_cells > 0) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
-    }
+    if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
     if (n_cells == 0) return AUCELL_OK;
+    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
+        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
+    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (!out_auc) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
-
-    SmemLayout L;
     const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
-    if (!plan_smem(p, key_bytes, OUT == OUT_AUC, &L))
-        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
-    int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * L.ctas_per_sm);
+    const int pos_bytes = p->pos16 ? 2 : 4;
 
-    CellArgs<ValT> a;
+    FusedArgs<ValT> a;
     memset(&a, 0, sizeof a);
+    int off = 0;
+    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
+    a.off_h2 = off; off = align16(off + (kCapF + 1) * 4);
+    a.off_fk = off; off = align16(off + kCapF * key_bytes);
+    a.off_fp = off; off = align16(off + kCapF * pos_bytes);
+    a.off_mixed = off; off = align16(off + kNb1 / 8);
+    a.off_bits = off; off = align16(off + p->n_words * 4);
+    a.off_wpre = off; off = align16(off + p->n_words * 4);
+    a.off_acc = off; off = align16(off + p->n_acc * 8);
+    const int smem = off;
+    if (smem > p->smem_optin)
+        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
+    const int per_sm = std::max<int>(1, std::min<int64_t>(2, (228 * 1024) / (smem + 1024)));
+    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * per_sm);
+
     a.dense = dense; a.row_stride = row_stride;
     a.indptr = indptr; a.indices = indices; a.data = data;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
     a.inv_perm = p->d_inv_perm;
     a.rank_cutoff = (int)p->rank_cutoff;
-    a.reg = reg_of(p);
-    a.out_rank = out_rank; a.out_auc = out_auc; a.out_nnz = out_nnz;
-    a.cap = L.cap;
-    a.off_key = L.off_key; a.off_pos = L.off_pos; a.off_bits = L.off_bits; a.off_wpre = L.off_wpre;
-    a.off_tbl = L.off_tbl;
+    a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
+    a.tab = tab_of(p);
+    a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.scratch_cap = next_pow2(p->n_genes);
-    if (L.cap < a.scratch_cap) {
-        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
-        if (rc) return rc;
-    }
-    if (p->pos16) return launch_cell<ValT, uint16_t, IN, OUT>(p, a, L, grid, st);
-    return launch_cell<ValT, uint32_t, IN, OUT>(p, a, L, grid, st);
+    int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
+    if (rc) return rc;
+    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, grid, st);
+    return launch_fused<ValT, uint32_t, IN>(p, a, smem, grid, st);
 }
 
 }  // namespace
@@ -331,52 +377,119 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
     if (n_regulons > 0) {
         const int64_t nnz = h_reg_indptr[n_regulons];
         p->reg_nnz = nnz;
-        std::vector<int32_t> indptr32((size_t)n_regulons + 1);
-        std::vector<int32_t> pos((size_t)std::max<int64_t>(nnz, 1));
-        std::vector<double> wts((size_t)std::max<int64_t>(nnz, 1));
-        std::vector<std::pair<int32_t, double>> ent;
+        p->acc64 = p->weighted || rank_cutoff > 65535;
+        // ---- accumulators and fixed-point weights (see cell_kernels.cuh, step 3) ------------------------
+        std::vector<int32_t> acc_first((size_t)n_regulons, -1);
+        std::vector<uint8_t> acc_parts((size_t)n_regulons, 0);
+        std::vector<double> acc_scale;
+        struct TEnt { int32_t pos; uint32_t acc; long long w; };
+        std::vector<TEnt> ents;
+        ents.reserve((size_t)nnz + 16);
         for (int r = 0; r < n_regulons; ++r) {
-            indptr32[r] = (int32_t)h_reg_indptr[r];
-            ent.clear();
-            for (int64_t e = h_reg_indptr[r]; e < h_reg_indptr[r + 1]; ++e) {
-                int32_t g = h_reg_cols[e];
-                if (g < 0 || g >= n_genes) {
+            const int64_t b = h_reg_indptr[r], e = h_reg_indptr[r + 1];
+            for (int64_t k = b; k < e; ++k) {
+                if (h_reg_cols[k] < 0 || h_reg_cols[k] >= n_genes) {
                     aucell_plan_destroy(p);
                     return fail(AUCELL_ERR_INVALID, "regulon gene column out of range");
                 }
-                ent.emplace_back(inv[g], h_reg_weights ? h_reg_weights[e] : 1.0);
             }
-            stagger_banks(ent, p->pos16);
-            for (size_t k = 0; k < ent.size(); ++k) {
-                pos[h_reg_indptr[r] + k] = ent[k].first;
-                wts[h_reg_indptr[r] + k] = ent[k].second;
-            }
-            if (h_reg_valid[r] && !(h_reg_max_auc[r] > 0.0)) {
+            if (!h_reg_valid[r]) continue;
+            if (!(h_reg_max_auc[r] > 0.0) || e == b) {
                 aucell_plan_destroy(p);
-                return fail(AUCELL_ERR_INVALID, "max_auc must be > 0 for valid regulons");
+                return fail(AUCELL_ERR_INVALID, "valid regulons need max_auc > 0 and at least one gene");
+            }
+            const int first = (int)acc_scale.size();
+            acc_first[r] = first;
+            if (!p->weighted) {
+                acc_parts[r] = 1;
+                acc_scale.push_back(1.0);
+                for (int64_t k = b; k < e; ++k) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first, 1ll});
+                continue;
+            }
+            // W = llrint(w * 2^s): |sum| <= hits * Wmax * cutoff must stay below 2^62
+            double wmax = 0.0, wmin = 0.0;
+            for (int64_t k = b; k < e; ++k) {
+                const double aw = std::fabs(h_reg_weights[k]);
+                if (!std::isfinite(aw)) {
+                    aucell_plan_destroy(p);
+                    return fail(AUCELL_ERR_INVALID, "regulon weights must be finite");
+                }
+                if (aw > 0.0) {
+                    wmax = std::max(wmax, aw);
+                    wmin = (wmin == 0.0) ? aw : std::min(wmin, aw);
+                }
+            }
+            if (wmax == 0.0) {  // all-zero weights cannot give max_auc > 0, but stay safe
+                acc_parts[r] = 1;
+                acc_scale.push_back(1.0);
+                continue;
+            }
+            const double hits = (double)std::min<int64_t>(e - b, std::max<int64_t>(rank_cutoff, 1));
+            int B = 62 - (int)std::ceil(std::log2(hits * (double)std::max<int64_t>(rank_cutoff, 1)));
+            B = std::max(24, std::min(B, 46));   // W is stored in 48 signed bits
+            int ex = 0;
+            std::frexp(wmax, &ex);                 // wmax = f * 2^ex, f in [0.5, 1)
+            const int s1 = B - ex;                 // wmax * 2^s1 in [2^(B-1), 2^B)
+            const bool wide = std::ldexp(wmin, s1) < 8388608.0;  // smallest weight keeps < 24 bits: add a 2nd limb
+            const int s2 = s1 + B - 1;
+            acc_parts[r] = wide ? 2 : 1;
+            acc_scale.push_back(std::ldexp(1.0, -s1));
+            if (wide) acc_scale.push_back(std::ldexp(1.0, -s2));
+            for (int64_t k = b; k < e; ++k) {
+                const double w = h_reg_weights[k];
+                const long long W1 = std::llrint(std::ldexp(w, s1));
+                if (W1 != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first, W1});
+                if (wide) {
+                    const double res = w - std::ldexp((double)W1, -s1);   // exact
+                    const long long W2 = std::llrint(std::ldexp(res, s2));
+                    if (W2 != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first + 1u, W2});
+                }
             }
         }
-        indptr32[n_regulons] = (int32_t)nnz;
-        PCK(cudaMalloc(&p->d_reg_indptr, sizeof(int32_t) * (n_regulons + 1)));
-        PCK(cudaMemcpy(p->d_reg_indptr, indptr32.data(), sizeof(int32_t) * (n_regulons + 1), cudaMemcpyHostToDevice));
-        const size_t nalloc = (size_t)std::max<int64_t>(nnz, 1);
-        if (p->pos16) {
-            std::vector<uint16_t> pos16v(nalloc);
-            for (int64_t e = 0; e < nnz; ++e) pos16v[e] = (uint16_t)pos[e];
-            PCK(cudaMalloc(&p->d_reg_pos, sizeof(uint16_t) * nalloc));
-            PCK(cudaMemcpy(p->d_reg_pos, pos16v.data(), sizeof(uint16_t) * nalloc, cudaMemcpyHostToDevice));
-        } else {
-            PCK(cudaMalloc(&p->d_reg_pos, sizeof(uint32_t) * nalloc));
-            PCK(cudaMemcpy(p->d_reg_pos, pos.data(), sizeof(uint32_t) * nalloc, cudaMemcpyHostToDevice));
+        p->n_acc = (int)acc_scale.size();
+        // ---- gene-major table T: counting sort of the entries by shuffled position --------------------
+        std::vector<uint32_t> tptr((size_t)n_genes + 1, 0u);
+        for (auto& t : ents) tptr[(size_t)t.pos + 1]++;
+        for (int64_t g = 0; g < n_genes; ++g) tptr[g + 1] += tptr[g];
+        const size_t nT = ents.size(), nalloc = std::max<size_t>(nT, 1);
+        std::vector<uint32_t> tacc(nalloc, 0u);
+        std::vector<long long> tw(nalloc, 0ll);
+        {
+            std::vector<uint32_t> cur(tptr.begin(), tptr.end() - 1);
+            for (auto& t : ents) {
+                const uint32_t at = cur[t.pos]++;
+                tacc[at] = t.acc;
+                tw[at] = t.w;
+            }
+        }
+        PCK(cudaMalloc(&p->d_tptr, sizeof(uint32_t) * (n_genes + 1)));
+        PCK(cudaMemcpy(p->d_tptr, tptr.data(), sizeof(uint32_t) * (n_genes + 1), cudaMemcpyHostToDevice));
+        if (p->n_acc > 65535) {
+            aucell_plan_destroy(p);
+            return fail(AUCELL_ERR_UNSUPPORTED, "more than 65535 regulon accumulators");
         }
         if (p->weighted) {
-            PCK(cudaMalloc(&p->d_reg_weight, sizeof(double) * nalloc));
-            PCK(cudaMemcpy(p->d_reg_weight, wts.data(), sizeof(double) * nalloc, cudaMemcpyHostToDevice));
+            std::vector<unsigned long long> tent(nalloc, 0ull);
+            for (size_t k = 0; k < nT; ++k)
+                tent[k] = ((unsigned long long)tw[k] << 16) | (unsigned long long)(tacc[k] & 0xFFFFu);
+            PCK(cudaMalloc(&p->d_tent, sizeof(unsigned long long) * nalloc));
+            PCK(cudaMemcpy(p->d_tent, tent.data(), sizeof(unsigned long long) * nalloc, cudaMemcpyHostToDevice));
+        } else {
+            std::vector<uint16_t> t16(nalloc, 0);
+            for (size_t k = 0; k < nT; ++k) t16[k] = (uint16_t)tacc[k];
+            PCK(cudaMalloc(&p->d_tacc16, sizeof(uint16_t) * nalloc));
+            PCK(cudaMemcpy(p->d_tacc16, t16.data(), sizeof(uint16_t) * nalloc, cudaMemcpyHostToDevice));
         }
+        const size_t nacc = std::max<size_t>(acc_scale.size(), 1);
+        acc_scale.resize(nacc, 1.0);
+        PCK(cudaMalloc(&p->d_acc_first, sizeof(int32_t) * n_regulons));
+        PCK(cudaMemcpy(p->d_acc_first, acc_first.data(), sizeof(int32_t) * n_regulons, cudaMemcpyHostToDevice));
+        PCK(cudaMalloc(&p->d_acc_parts, n_regulons));
+        PCK(cudaMemcpy(p->d_acc_parts, acc_parts.data(), n_regulons, cudaMemcpyHostToDevice));
+        PCK(cudaMalloc(&p->d_acc_scale, sizeof(double) * nacc));
+        PCK(cudaMemcpy(p->d_acc_scale, acc_scale.data(), sizeof(double) * nacc, cudaMemcpyHostToDevice));
         PCK(cudaMalloc(&p->d_reg_max_auc, sizeof(double) * n_regulons));
         PCK(cudaMemcpy(p->d_reg_max_auc, h_reg_max_auc, sizeof(double) * n_regulons, cudaMemcpyHostToDevice));
-        PCK(cudaMalloc(&p->d_reg_valid, n_regulons));
-        PCK(cudaMemcpy(p->d_reg_valid, h_reg_valid, n_regulons, cudaMemcpyHostToDevice));
     }
 #undef PCK
     *out_plan = p;
@@ -387,11 +500,13 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     if (!p) return AUCELL_OK;
     DeviceGuard dg(p->device);
     cudaFree(p->d_inv_perm);
-    cudaFree(p->d_reg_indptr);
-    cudaFree(p->d_reg_pos);
-    cudaFree(p->d_reg_weight);
+    cudaFree(p->d_tptr);
+    cudaFree(p->d_tent);
+    cudaFree(p->d_tacc16);
+    cudaFree(p->d_acc_first);
+    cudaFree(p->d_acc_parts);
+    cudaFree(p->d_acc_scale);
     cudaFree(p->d_reg_max_auc);
-    cudaFree(p->d_reg_valid);
     for (auto& kv : p->scratch) cudaFree(kv.second.first);
     delete p;
     return AUCELL_OK;
@@ -400,47 +515,39 @@ int aucell_plan_destroy(aucell_plan_t* p) {
 // ---- create_rankings ---------------------------------------------------------------------------------
 int aucell_rank_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
                           uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream) {
-    return run_cells<float, IN_DENSE, OUT_RANK>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells,
-                                                 d_out_rank, nullptr, d_out_nnz, stream);
+    return run_rank<float, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
                           uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream) {
-    return run_cells<double, IN_DENSE, OUT_RANK>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells,
-                                                  d_out_rank, nullptr, d_out_nnz, stream);
+    return run_rank<double, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                         const float* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
                         void* stream) {
-    return run_cells<float, IN_CSR, OUT_RANK>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank,
-                                               nullptr, d_out_nnz, stream);
+    return run_rank<float, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                         const double* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
                         void* stream) {
-    return run_cells<double, IN_CSR, OUT_RANK>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank,
-                                                nullptr, d_out_nnz, stream);
+    return run_rank<double, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
 }
 
 // ---- fused aucell ------------------------------------------------------------------------------------
 int aucell_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
                      double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_cells<float, IN_DENSE, OUT_AUC>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, nullptr,
-                                                d_out_auc, d_out_nnz, stream);
+    return run_fused<float, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_auc, d_out_nnz, stream);
 }
 int aucell_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
                      double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_cells<double, IN_DENSE, OUT_AUC>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, nullptr,
-                                                 d_out_auc, d_out_nnz, stream);
+    return run_fused<double, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_auc, d_out_nnz, stream);
 }
 int aucell_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                    const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_cells<float, IN_CSR, OUT_AUC>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, nullptr,
-                                              d_out_auc, d_out_nnz, stream);
+    return run_fused<float, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
 int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                    const double* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_cells<double, IN_CSR, OUT_AUC>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, nullptr,
-                                               d_out_auc, d_out_nnz, stream);
+    return run_fused<double, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
 
 // ---- aucell4r ----------------------------------------------------------------------------------------
@@ -454,24 +561,19 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem = align16(p->n_genes * (p->pos16 ? 2 : 4));
-    if (smem > p->smem_optin) return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
-    const int per_sm = std::max<int>(1, std::min<int64_t>(4, (228 * 1024) / (smem + 1024)));
-    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * per_sm);
-    RegulonsDev reg = reg_of(p);
-#define LAUNCH_FR(PosT, W)                                                                              \
-    do {                                                                                                \
-        auto k = aucell_from_rankings_kernel<PosT, W>;                                                  \
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
-        k<<<grid, kBlock, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, \
-                                      d_out_auc);                                                       \
-    } while (0)
-    if (p->pos16) {
-        if (p->weighted) LAUNCH_FR(uint16_t, true); else LAUNCH_FR(uint16_t, false);
+    const int smem = align16(p->n_acc * 8);
+    if (smem > p->smem_optin) return fail(AUCELL_ERR_UNSUPPORTED, "too many regulons for the shared-memory accumulators");
+    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * 8);
+    GeneTableDev reg = tab_of(p);
+    if (p->acc64) {
+        auto k = aucell_from_rankings_kernel<true>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, kF, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, d_out_auc);
     } else {
-        if (p->weighted) LAUNCH_FR(uint32_t, true); else LAUNCH_FR(uint32_t, false);
+        auto k = aucell_from_rankings_kernel<false>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, kF, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, d_out_auc);
     }
-#undef LAUNCH_FR
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
     return AUCELL_OK;

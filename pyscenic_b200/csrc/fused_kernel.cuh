@@ -1,0 +1,611 @@
+// fused_kernel.cuh -- the AUCell hot path: per-cell ranking fused with the recovery-curve AUC of every regulon.
+//
+// Reference: pyscenic.aucell.aucell = aucell4r(create_rankings(exp_mtx, seed), ...)   src/pyscenic/aucell.py:185-213
+//            create_rankings  (pandas sample + rank(method="first", ascending=False))  src/pyscenic/aucell.py:25-51
+//            ctxcore.recovery.enrichment4cells -> aucs -> auc2d -> weighted_auc1d     (third-party)
+//
+// One CTA (kF threads) per cell, grid-stride.  The cells x genes ranking matrix is never formed: only genes ranked
+// below rank_cutoff contribute, AUC_r = sum_{g in r, rank_g < cutoff} w_g * (cutoff - rank_g) / max_auc_r
+// (closed form of weighted_auc1d's sum(diff(x) * cumsum(w)) / max_auc).
+//
+// Per cell:
+//   LOAD     the cell's explicit entries (values whose key != KEY_ZERO) live in REGISTERS, kItems per thread:
+//            (key, shuffled position).  Zeros stay implicit (rank n_gt + #zeros at smaller positions).
+//   RANK     positives are ranked by a two-level bucket sort on 32-bit shared atomics:
+//              level 1: value bins over the cell's own key range (ascending key = descending value);
+//                       bins starting at or beyond the cutoff are dropped;
+//              level 2: a bin with ONE distinct key (tie group) is split by shuffled position into as many
+//                       sub-buckets as it has entries (positions are uniform -> ~1 entry each); a bin with
+//                       several keys stays one sub-bucket;
+//              exact:   entries are stored in sub-bucket order and each counts the members of its own sub-bucket
+//                       that sort before it:  rank = base2[sub] + count.
+//            Crowded sub-buckets (many distinct keys in one value bin), negatives ranked below the cutoff, or
+//            more entries than kF * kItems send the cell to the general path (bitonic sort in global scratch).
+//   SCATTER  for each gene below the cutoff walk the gene-major regulon table T[pos] and add W * (cutoff - rank)
+//            into 64-bit integer accumulators in shared memory (32-bit atomics + carry; fixed-point weights).
+//            Integer adds commute, so the result does not depend on the order the atomics retire in.
+//   ZEROS    when fewer than `cutoff` genes are positive, zeros fill the remaining ranks in position order
+//            (bitmap of occupied positions + prefix popcount).
+//   OUT      out[cell, r] = (double(acc) * 2^-s) / max_auc[r], coalesced.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cell_kernels.cuh"
+#include "keys.cuh"
+
+namespace aucell {
+
+constexpr int kF = 512;                 // threads per CTA of the fused kernel
+constexpr int kFWarps = kF / 32;
+constexpr int kItems = 8;               // register-resident entries per thread
+constexpr int kCapF = kF * kItems;      // 4096 explicit entries per cell on the fast path
+constexpr int kNb1Log = 11;             // level-1 value bins
+constexpr int kNb1 = 1 << kNb1Log;
+constexpr int kMaxSub = 40;             // sub-bucket occupancy beyond which the cell goes to the general path
+
+// Gene-major regulon table with packed entries, indexed by shuffled position.
+struct GeneTableDev {
+    int n_regulons;
+    int n_acc;
+    const uint32_t* tptr;               // [n_genes + 1]
+    const unsigned long long* tent;     // weighted: [nnz] (W << 16) | accumulator   (W signed 48-bit fixed point)
+    const uint16_t* tacc16;             // unweighted: [nnz] accumulator
+    const int32_t* acc_first;           // [R] first accumulator of regulon r, -1 = invalid regulon
+    const uint8_t* acc_parts;           // [R] 1 or 2
+    const double* acc_scale;            // [n_acc]
+    const double* max_auc;              // [R]
+};
+
+template <typename ValT>
+struct FusedArgs {
+    const ValT* dense;                  // IN_DENSE
+    int64_t row_stride;
+    const int64_t* indptr;              // IN_CSR
+    const int32_t* indices;
+    const ValT* data;
+    int64_t n_cells;
+    int n_genes;
+    int n_words;
+    const int32_t* inv_perm;
+    int rank_cutoff;
+    uint32_t inv_ng;                    // ceil(2^32 / n_genes)
+    GeneTableDev tab;
+    double* out_auc;
+    int32_t* out_nnz;
+    // dynamic shared memory carve-up
+    int off_h1, off_h2, off_fk, off_fp, off_mixed, off_bits, off_wpre, off_acc;
+    // global scratch for the general path: per CTA scratch_cap (key, pos) pairs
+    void* scratch_key;
+    void* scratch_pos;
+    int scratch_cap;
+};
+
+template <int NT>
+__device__ __forceinline__ int block_excl_scan_n(int v, int* s_warp, int& total) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < NW) ? s_warp[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= o) xi += t;
+        }
+        s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const int res = s_warp[w] + incl - v;
+    __syncthreads();
+    return res;
+}
+
+// W * mval into accumulator(s) of every regulon holding the gene at shuffled position p.
+template <bool ACC64>
+__device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
+                                               uint32_t* __restrict__ acc_hi, unsigned p, unsigned mval) {
+    const uint32_t b = __ldg(t.tptr + p), e = __ldg(t.tptr + p + 1);
+    if (ACC64) {
+        if (t.tent != nullptr) {
+            for (uint32_t j = b; j < e; ++j) {
+                const unsigned long long ent = __ldg(t.tent + j);
+                const uint32_t r = (uint32_t)(ent & 0xFFFFull);
+                const long long w = ((long long)ent) >> 16;
+                const unsigned long long c = (unsigned long long)(w * (long long)mval);
+                const uint32_t lo = (uint32_t)c;
+                uint32_t hi = (uint32_t)(c >> 32);
+                const uint32_t old = atomicAdd(&acc_lo[r], lo);
+                hi += (old + lo < old) ? 1u : 0u;
+                if (hi) atomicAdd(&acc_hi[r], hi);
+            }
+        } else {  // unit weights but a cutoff too large for 32-bit sums
+            for (uint32_t j = b; j < e; ++j) {
+                const uint32_t r = __ldg(t.tacc16 + j);
+                const uint32_t old = atomicAdd(&acc_lo[r], mval);
+                if (old + mval < old) atomicAdd(&acc_hi[r], 1u);
+            }
+        }
+    } else {
+        for (uint32_t j = b; j < e; ++j) atomicAdd(&acc_lo[__ldg(t.tacc16 + j)], mval);
+    }
+}
+
+template <bool ACC64, int NT>
+__device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
+                                                  uint32_t* __restrict__ acc_hi, double* __restrict__ out) {
+    for (int r = threadIdx.x; r < t.n_regulons; r += NT) {
+        const int f = __ldg(t.acc_first + r);
+        double res = 0.0;
+        if (f >= 0) {
+            const int parts = __ldg(t.acc_parts + r);
+            double sum = 0.0;
+            for (int k = 0; k < parts; ++k) {
+                if (ACC64) {
+                    const long long v = (long long)(((unsigned long long)acc_hi[f + k] << 32) | acc_lo[f + k]);
+                    sum += (double)v * __ldg(t.acc_scale + f + k);
+                    acc_hi[f + k] = 0u;
+                } else {
+                    sum += (double)acc_lo[f + k];
+                }
+                acc_lo[f + k] = 0u;
+            }
+            res = __ddiv_rn(sum, __ldg(t.max_auc + r));
+        }
+        out[r] = res;
+    }
+}
+
+// ---- general path: all explicit entries of the cell into global scratch, bitonic sort, scatter --------------
+template <typename ValT, typename PosT, int IN, bool ACC64>
+__device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s_bits, uint32_t* s_wpre,
+                             uint32_t* acc_lo, uint32_t* acc_hi, int* s_cnt, int* s_scan) {
+    using KT = KeyOf<ValT>;
+    using KeyT = typename KT::type;
+    const int tid = threadIdx.x, lane = tid & 31;
+    KeyT* lk = reinterpret_cast<KeyT*>(a.scratch_key) + (size_t)blockIdx.x * a.scratch_cap;
+    PosT* lp = reinterpret_cast<PosT*>(a.scratch_pos) + (size_t)blockIdx.x * a.scratch_cap;
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+    int64_t count;
+    const ValT* vals;
+    const int32_t* cols = nullptr;
+    if (IN == IN_DENSE) {
+        count = a.n_genes;
+        vals = a.dense + cell * a.row_stride;
+    } else {
+        const int64_t begin = a.indptr[cell];
+        count = a.indptr[cell + 1] - begin;
+        vals = a.data + begin;
+        cols = a.indices + begin;
+    }
+    for (int64_t base = 0; base < count; base += kF) {
+        const int64_t i = base + tid;
+        const bool in = i < count;
+        KeyT key = KT::KEY_ZERO;
+        if (in) key = KT::make(vals[i]);
+        const bool pred = in && key != KT::KEY_ZERO;
+        const unsigned mk = __ballot_sync(0xffffffffu, pred);
+        const unsigned mgt = __ballot_sync(0xffffffffu, pred && key < KT::KEY_ZERO);
+        if (mk) {
+            int wbase = 0;
+            const int leader = __ffs(mk) - 1;
+            if (lane == leader) {
+                wbase = atomicAdd(&s_cnt[0], __popc(mk));
+                if (mgt) atomicAdd(&s_cnt[1], __popc(mgt));
+            }
+            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+            if (pred) {
+                const int idx = wbase + __popc(mk & lanemask_lt());
+                const int g = (IN == IN_DENSE) ? (int)i : cols[i];
+                lk[idx] = key;
+                lp[idx] = (PosT)a.inv_perm[g];
+            }
+        }
+    }
+    __syncthreads();
+    const int m = s_cnt[0], n_gt = s_cnt[1];
+    const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
+    const int n_zero = n_genes - m;
+    int P = 2;
+    while (P < m) P <<= 1;
+    for (int i = m + tid; i < P; i += kF) {
+        lk[i] = KT::KEY_NAN;
+        lp[i] = (PosT)~(PosT)0;
+    }
+    // bitonic sort by (key, position); pairs are unique so the result is order-independent
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < (P >> 1); t += kF) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                const KeyT ka = lk[lo], kb = lk[hi];
+                const PosT pa = lp[lo], pb = lp[hi];
+                const bool gt = (ka > kb) || (ka == kb && pa > pb);
+                if (gt == asc) {
+                    lk[lo] = kb; lk[hi] = ka;
+                    lp[lo] = pb; lp[hi] = pa;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int top_pos = min(n_gt, cutoff);
+    for (int i = tid; i < top_pos; i += kF)
+        scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - i));
+    const int q_zero = cutoff - n_gt;
+    if (q_zero > 0) {
+        for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
+        __syncthreads();
+        for (int i = tid; i < m; i += kF) {
+            const unsigned p = (unsigned)lp[i];
+            atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+        }
+        __syncthreads();
+        const int per = (a.n_words + kF - 1) / kF;
+        const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
+        int local = 0;
+        for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
+        int total;
+        int run = block_excl_scan_n<kF>(local, s_scan, total);
+        for (int w = w0; w < w1; ++w) {
+            s_wpre[w] = (uint32_t)run;
+            run += __popc(s_bits[w]);
+        }
+        __syncthreads();
+        for (int p = tid; p < n_genes; p += kF) {
+            const int w = p >> 5;
+            const uint32_t bw = s_bits[w];
+            const int z0 = (w << 5) - (int)s_wpre[w];
+            if (z0 >= q_zero) break;                    // words are visited in increasing order by every thread
+            if (!((bw >> (p & 31)) & 1u)) {
+                const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
+                if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+            }
+        }
+        const int q_neg = q_zero - n_zero;
+        const int neg_end = q_neg > 0 ? min(m, n_gt + q_neg) : n_gt;
+        for (int i = n_gt + tid; i < neg_end; i += kF)
+            scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - (i + n_zero)));
+    }
+    if (a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
+}
+
+// ---- the fused kernel ---------------------------------------------------------------------------------------
+template <typename ValT, typename PosT, int IN, bool ACC64>
+__global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<ValT> a) {
+    using KT = KeyOf<ValT>;
+    using KeyT = typename KT::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* const h1 = reinterpret_cast<uint32_t*>(smem + a.off_h1);      // [kNb1 + 1]
+    uint32_t* const h2 = reinterpret_cast<uint32_t*>(smem + a.off_h2);      // [kCapF + 1]
+    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);              // [kCapF] bucket-ordered keys
+    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);              // [kCapF] bucket-ordered positions
+    KeyT* const rep = fk;                                                   // [kNb1] alias: dead before fk is written
+    uint32_t* const mixed = reinterpret_cast<uint32_t*>(smem + a.off_mixed);  // [kNb1 / 32]
+    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem + a.off_bits);
+    uint32_t* const s_wpre = reinterpret_cast<uint32_t*>(smem + a.off_wpre);
+    uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem + a.off_acc);
+    uint32_t* const acc_hi = acc_lo + a.tab.n_acc;
+    __shared__ int s_scan[33];
+    __shared__ int s_cnt[2];
+    __shared__ int s_red_i[2][kFWarps];
+    __shared__ KeyT s_red_k[2][kFWarps];
+    __shared__ int s_flag[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
+
+    for (int i = tid; i < 2 * a.tab.n_acc; i += kF) acc_lo[i] = 0u;
+    __syncthreads();
+
+    for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
+        // ---------------- LOAD: explicit entries into registers ----------------------------------------------
+        KeyT key[kItems];
+        PosT pos[kItems];
+        int m_total;                      // explicit entries of the cell
+        bool general = false;
+        if (IN == IN_CSR) {
+            const int64_t begin = a.indptr[cell];
+            const int64_t count = a.indptr[cell + 1] - begin;
+            general = count > kCapF;
+            if (!general) {
+                const ValT* __restrict__ vals = a.data + begin;
+                const int32_t* __restrict__ cols = a.indices + begin;
+                ValT v[kItems];
+                int c[kItems];
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    const int i = k * kF + tid;
+                    const bool in = i < (int)count;
+                    v[k] = in ? vals[i] : (ValT)0;
+                    c[k] = in ? cols[i] : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    key[k] = KT::make(v[k]);
+                    pos[k] = (key[k] != KT::KEY_ZERO) ? (PosT)__ldg(a.inv_perm + c[k]) : (PosT)0;
+                }
+            }
+            m_total = 0;
+        } else {
+            // dense row: compact the non-zero values through shared memory (fk/fp as staging), then to registers
+            if (tid == 0) s_cnt[0] = 0;
+            __syncthreads();
+            const ValT* __restrict__ row = a.dense + cell * a.row_stride;
+            for (int base = 0; base < n_genes; base += kF) {
+                const int g = base + tid;
+                KeyT kk = KT::KEY_ZERO;
+                if (g < n_genes) kk = KT::make(row[g]);
+                const bool pred = kk != KT::KEY_ZERO;
+                const unsigned mk = __ballot_sync(0xffffffffu, pred);
+                if (mk) {
+                    int wbase = 0;
+                    const int leader = __ffs(mk) - 1;
+                    if (lane == leader) wbase = atomicAdd(&s_cnt[0], __popc(mk));
+                    wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                    const int idx = wbase + __popc(mk & lanemask_lt());
+                    if (pred && idx < kCapF) {
+                        fk[idx] = kk;
+                        fp[idx] = (PosT)__ldg(a.inv_perm + g);
+                    }
+                }
+            }
+            __syncthreads();
+            m_total = s_cnt[0];
+            general = m_total > kCapF;
+            if (!general) {
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    const int i = k * kF + tid;
+                    key[k] = (i < m_total) ? fk[i] : KT::KEY_ZERO;
+                    pos[k] = (i < m_total) ? fp[i] : (PosT)0;
+                }
+            }
+            __syncthreads();              // staging is free again (rep / fk are rewritten below)
+        }
+
+        int n_gt = 0, m = 0;
+        if (!general) {
+            // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------
+            int c_exp = 0, c_pos = 0;
+            KeyT kmin = KT::KEY_ZERO, kmax = 0;
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
+                if (key[k] < KT::KEY_ZERO) {
+                    ++c_pos;
+                    kmin = tmin(kmin, key[k]);
+                    kmax = tmax(kmax, key[k]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c_exp += __shfl_xor_sync(0xffffffffu, c_exp, o);
+                c_pos += __shfl_xor_sync(0xffffffffu, c_pos, o);
+                kmin = tmin(kmin, (KeyT)__shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = tmax(kmax, (KeyT)__shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            if (lane == 0) {
+                s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
+                s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
+            }
+            // clear the level-1 histogram while we are at it
+            for (int b = tid; b <= kNb1; b += kF) h1[b] = 0u;
+            if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
+            if (tid == 0) s_flag[0] = 0;
+            __syncthreads();
+            {
+                int e = s_red_i[0][lane & (kFWarps - 1)], p = s_red_i[1][lane & (kFWarps - 1)];
+                KeyT mn = s_red_k[0][lane & (kFWarps - 1)], mx = s_red_k[1][lane & (kFWarps - 1)];
+#pragma unroll
+                for (int o = kFWarps / 2; o > 0; o >>= 1) {
+                    e += __shfl_xor_sync(0xffffffffu, e, o);
+                    p += __shfl_xor_sync(0xffffffffu, p, o);
+                    mn = tmin(mn, (KeyT)__shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = tmax(mx, (KeyT)__shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                m = e; n_gt = p; kmin = mn; kmax = mx;
+            }
+            const int n_zero = n_genes - m;
+            if (cutoff - n_gt - n_zero > 0) general = true;      // negatives rank below the cutoff: general path
+
+            if (!general && n_gt > 0) {
+                // ---------------- RANK: two-level bucket sort of the positives ------------------------------
+                const KeyT range = kmax - kmin;
+                int nbits = 0;
+                if (range) nbits = (sizeof(KeyT) == 8) ? 64 - __clzll((long long)range) : 32 - __clz((int)range);
+                const int shift = max(0, nbits - kNb1Log);
+                uint32_t bin[kItems];
+                // S1: level-1 histogram, one representative key per bin
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    bin[k] = 0xFFFFFFFFu;
+                    if (key[k] < KT::KEY_ZERO) {
+                        bin[k] = (uint32_t)((key[k] - kmin) >> shift);
+                        atomicAdd(&h1[bin[k]], 1u);
+                        rep[bin[k]] = key[k];
+                    }
+                }
+                __syncthreads();
+                // S2: mixed bins; exclusive scan of bin counts; n_s = entries in bins that start below the cutoff
+#pragma unroll
+                for (int k = 0; k < kItems; ++k)
+                    if (bin[k] != 0xFFFFFFFFu && rep[bin[k]] != key[k])
+                        atomicOr(&mixed[bin[k] >> 5], 1u << (bin[k] & 31));
+                {
+                    constexpr int per = kNb1 / kF;
+                    const int b0 = tid * per;
+                    int cnt[per];
+                    int local = 0;
+#pragma unroll
+                    for (int j = 0; j < per; ++j) { cnt[j] = (int)h1[b0 + j]; local += cnt[j]; }
+                    int total;
+                    int run = block_excl_scan_n<kF>(local, s_scan, total);
+                    if (tid == 0) s_flag[1] = n_gt;
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < per; ++j) {
+                        h1[b0 + j] = (uint32_t)run;
+                        if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];
+                        run += cnt[j];
+                    }
+                    if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
+                }
+                __syncthreads();
+                const int n_s = s_flag[1];
+                // S3: clear level-2 histogram
+                for (int b = tid; b <= n_s; b += kF) h2[b] = 0u;
+                __syncthreads();
+                // S4: level-2 histogram
+                uint32_t sbs[kItems];     // (sub-bucket << 8) | arrival slot ; 0xFFFFFFFF = dropped
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    sbs[k] = 0xFFFFFFFFu;
+                    if (bin[k] != 0xFFFFFFFFu) {
+                        const uint32_t base = h1[bin[k]];
+                        if ((int)base < cutoff) {
+                            const uint32_t c = h1[bin[k] + 1] - base;
+                            uint32_t sub = 0;
+                            if (!((mixed[bin[k] >> 5] >> (bin[k] & 31)) & 1u)) {
+                                sub = (uint32_t)(((unsigned long long)((unsigned)pos[k]) * c * a.inv_ng) >> 32);
+                                sub = min(sub, c - 1u);
+                            }
+                            const uint32_t sb = base + sub;
+                            const uint32_t got = atomicAdd(&h2[sb], 1u);
+                            if (got >= (uint32_t)kMaxSub) s_flag[0] = 1;
+                            sbs[k] = (sb << 8) | min(got, 255u);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (s_flag[0]) {
+                    general = true;       // crowded sub-bucket (uniform decision: read after the barrier)
+                } else {
+                    // S5: exclusive scan of level-2 counts
+                    {
+                        const int per = (n_s + kF - 1) / kF;
+                        const int b0 = tid * per, b1 = min(b0 + per, n_s);
+                        int local = 0;
+                        for (int b = b0; b < b1; ++b) local += (int)h2[b];
+                        int total;
+                        int run = block_excl_scan_n<kF>(local, s_scan, total);
+                        for (int b = b0; b < b1; ++b) {
+                            const int c = (int)h2[b];
+                            h2[b] = (uint32_t)run;
+                            run += c;
+                        }
+                        if (tid == 0) h2[n_s] = (uint32_t)n_s;
+                    }
+                    __syncthreads();
+                    // S6: entries into sub-bucket order (sub-buckets starting at or beyond the cutoff are dropped)
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k) {
+                        if (sbs[k] != 0xFFFFFFFFu) {
+                            const uint32_t b2 = h2[sbs[k] >> 8];
+                            if ((int)b2 < cutoff) {
+                                fk[b2 + (sbs[k] & 255u)] = key[k];
+                                fp[b2 + (sbs[k] & 255u)] = pos[k];
+                            } else {
+                                sbs[k] = 0xFFFFFFFFu;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // S7: exact rank inside the sub-bucket, then scatter
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k) {
+                        if (sbs[k] != 0xFFFFFFFFu) {
+                            const uint32_t sb = sbs[k] >> 8;
+                            const uint32_t b = h2[sb], e = h2[sb + 1];
+                            uint32_t rank = b;
+                            for (uint32_t j = b; j < e; ++j) {
+                                const KeyT ko = fk[j];
+                                rank += (ko < key[k] || (ko == key[k] && fp[j] < pos[k])) ? 1u : 0u;
+                            }
+                            if ((int)rank < cutoff)
+                                scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)pos[k], (unsigned)(cutoff - (int)rank));
+                        }
+                    }
+                }
+            }
+            if (!general && n_gt < cutoff) {
+                // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -------------------------
+                const int q_zero = cutoff - n_gt;
+                for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < kItems; ++k)
+                    if (key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
+                __syncthreads();
+                const int per = (a.n_words + kF - 1) / kF;
+                const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
+                int local = 0;
+                for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
+                int total;
+                int run = block_excl_scan_n<kF>(local, s_scan, total);
+                for (int w = w0; w < w1; ++w) {
+                    s_wpre[w] = (uint32_t)run;
+                    run += __popc(s_bits[w]);
+                }
+                __syncthreads();
+                for (int p = tid; p < n_genes; p += kF) {
+                    const int w = p >> 5;
+                    const uint32_t bw = s_bits[w];
+                    const int z0 = (w << 5) - (int)s_wpre[w];
+                    if (z0 >= q_zero) break;
+                    if (!((bw >> (p & 31)) & 1u)) {
+                        const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
+                        if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+                    }
+                }
+            }
+            if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
+        }
+        if (general) {
+            __syncthreads();
+            general_cell<ValT, PosT, IN, ACC64>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan);
+        }
+        __syncthreads();
+        write_aucs_packed<ACC64, kF>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);
+        __syncthreads();
+    }
+}
+
+// aucell4r path: AUCs from an existing ranking matrix (reference aucell.py:98-182; ctxcore auc2d): the same
+// scatter, driven straight from the ranking row (T is indexed by the ranking matrix' own columns).
+template <bool ACC64>
+__global__ void __launch_bounds__(kF) aucell_from_rankings_kernel(const uint32_t* __restrict__ rnk, int64_t n_cells,
+                                                                  int64_t row_stride, int n_genes, int cutoff,
+                                                                  GeneTableDev tab, double* __restrict__ out_auc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* const acc_hi = acc_lo + tab.n_acc;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * tab.n_acc; i += kF) acc_lo[i] = 0u;
+    __syncthreads();
+    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const uint32_t* row = rnk + cell * row_stride;
+        for (int j = tid; j < n_genes; j += kF) {
+            const uint32_t r = row[j];
+            if (r < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)j, (uint32_t)cutoff - r);
+        }
+        __syncthreads();
+        write_aucs_packed<ACC64, kF>(tab, acc_lo, acc_hi, out_auc + cell * (int64_t)tab.n_regulons);
+        __syncthreads();
+    }
+}
+
+}  // namespace aucell

@@ -267,6 +267,40 @@ def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted):
     assert np.array_equal(nnz_d.cpu().numpy(), np.count_nonzero(X, axis=1))
 
 
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_fast_path_and_its_fallback(unweighted):
+    """The bucket-sort fast path and the cells it must hand to the general sort: many distinct near-equal values
+    sharing one value bin (crowded bucket), binary data (one tie group), all-distinct data, a +inf outlier."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(77)
+    n_cells, n_genes = 64, 6000
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)      # 299
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.2)
+    idx = rs.choice(n_genes, 900, replace=False)
+    X[0] = 0.0; X[0, idx] = (1.0 + np.arange(900) * 1e-6).astype(np.float32); X[0, idx[0]] = 1e6   # crowded bin
+    X[1] = (rs.rand(n_genes) < 0.3).astype(np.float32)                       # binary: one tie group
+    X[2] = 0.0; X[2, idx] = rs.rand(900).astype(np.float32) + 0.5             # all distinct
+    X[3, 5] = np.inf
+    X[4] = 0.0; X[4, idx[:400]] = 2.0; X[4, idx[400:]] = np.nextafter(np.float32(2.0), np.float32(3.0))  # 2 keys, 1 bin
+    X[5] = 0.0; X[5, idx[:50]] = np.float32(1e-45)                            # denormals only, n_pos < cutoff
+    X[6] = np.abs(rs.randn(n_genes)).astype(np.float32) + 1.0                 # dense positive: list overflow
+    reg = synth.make_regulons(rs, n_genes, 50, 10, 400, weighted=True)
+    perm = np.random.RandomState(5).permutation(n_genes)
+    want = oracle_auc(X, perm, reg, cutoff, unweighted)
+    csr = sp.csr_matrix(X)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted) as plan:
+        got_d = plan.aucell_dense(cuda(X)).cpu().numpy()
+        got_s = plan.aucell_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.int32)),
+                                cuda(csr.data)).cpu().numpy()
+        got_64 = plan.aucell_dense(cuda(X.astype(np.float64))).cpu().numpy()
+    assert np.array_equal(got_d, got_s) and np.array_equal(got_d, got_64)
+    if unweighted:
+        assert np.array_equal(got_d, want)
+    else:
+        assert_auc_close(got_d, want)
+
+
 def test_fused_csr_config3_shape_vs_oracle():
     """BASELINE.json configs[2] shape at oracle-friendly scale: 25k genes CSR ~7 % nnz, 500 regulons incl.
     repressor (-) regulons, weighted; per-cell nnz log-normal so some cells sit below the cutoff of 1,249."""
