@@ -282,6 +282,7 @@ def run_ours(args, rank, world, local_rank):
     ms = ev0.elapsed_time(ev1)
     launches = _native.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    path_stats = plan.path_stats()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -384,6 +385,7 @@ def run_ours(args, rank, world, local_rank):
                          "bytes_per_cell": alg_bytes / n_cells},
             "cpu_baseline": cpu_baseline,
             "parity": parity,
+            "path_stats": path_stats,
         }
         print(json.dumps(line), flush=True)
     plan.close()

@@ -128,6 +128,10 @@ int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
 
 /* ---- instrumentation -------------------------------------------------------------------------------- */
+/* Which code path the fused kernel took, summed over every call on this plan since the last reset (synchronises
+ * the device): out5 = { cells, general path: more than 4096 explicit entries, general path: negative values ranked
+ * below the cutoff, general path: crowded value bin, cells that needed zeros below the cutoff }. */
+int aucell_plan_path_stats(const aucell_plan_t* plan, uint64_t* out5, int reset);
 /* number of kernels this library has launched on the calling process since load (bench.py gpu_launches) */
 int64_t aucell_b200_launch_count(void);
 

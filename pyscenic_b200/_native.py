@@ -53,6 +53,7 @@ EXPORTED_SYMBOLS = [
     "aucell_csr_f32_host",
     "aucell_dense_f32_host",
     "aucell_b200_launch_count",
+    "aucell_plan_path_stats",
 ]
 
 
@@ -139,6 +140,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_b200_launch_count.restype = i64
         lib.aucell_plan_create.argtypes = [c_int, i64, p, i32, p, p, p, p, p, i64, p]
         lib.aucell_plan_create.restype = c_int
+        lib.aucell_plan_path_stats.argtypes = [p, p, c_int]
+        lib.aucell_plan_path_stats.restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]
         lib.aucell_plan_destroy.restype = c_int
         for name in ("aucell_rank_dense_f32", "aucell_rank_dense_f64"):

@@ -86,6 +86,7 @@ struct aucell_plan {
     uint8_t* d_acc_parts = nullptr;
     double* d_acc_scale = nullptr;
     double* d_reg_max_auc = nullptr;
+    unsigned long long* d_stats = nullptr;   // path statistics of the fused kernel (5 counters)
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;
     mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
@@ -251,9 +252,14 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     int off = 0;
     a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
     a.off_h2 = off; off = align16(off + (kCapF + 1) * 4);
-    a.off_fk = off; off = align16(off + kCapF * key_bytes);
+    a.off_fk = off; off = align16(off + kCapF * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
     a.off_fp = off; off = align16(off + kCapF * pos_bytes);
     a.off_mixed = off; off = align16(off + kNb1 / 8);
+    {
+        int g = 2;
+        while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
+        a.gen_cap = g;
+    }
     a.off_bits = off; off = align16(off + p->n_words * 4);
     a.off_wpre = off; off = align16(off + p->n_words * 4);
     a.off_acc = off; off = align16(off + p->n_acc * 8);
@@ -271,6 +277,7 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
     a.tab = tab_of(p);
     a.out_auc = out_auc; a.out_nnz = out_nnz;
+    a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
     int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
     if (rc) return rc;
@@ -371,6 +378,8 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
         }                                                              \
     } while (0)
 
+    PCK(cudaMalloc(&p->d_stats, 8 * sizeof(unsigned long long)));
+    PCK(cudaMemset(p->d_stats, 0, 8 * sizeof(unsigned long long)));
     PCK(cudaMalloc(&p->d_inv_perm, sizeof(int32_t) * n_genes));
     PCK(cudaMemcpy(p->d_inv_perm, inv.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice));
 
@@ -499,6 +508,7 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
 int aucell_plan_destroy(aucell_plan_t* p) {
     if (!p) return AUCELL_OK;
     DeviceGuard dg(p->device);
+    cudaFree(p->d_stats);
     cudaFree(p->d_inv_perm);
     cudaFree(p->d_tptr);
     cudaFree(p->d_tent);
@@ -509,6 +519,16 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_reg_max_auc);
     for (auto& kv : p->scratch) cudaFree(kv.second.first);
     delete p;
+    return AUCELL_OK;
+}
+
+int aucell_plan_path_stats(const aucell_plan_t* p, uint64_t* out5, int reset) {
+    if (!p || !out5) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out5, p->d_stats, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(p->d_stats, 0, 8 * sizeof(unsigned long long)));
     return AUCELL_OK;
 }
 

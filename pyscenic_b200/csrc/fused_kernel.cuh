@@ -75,11 +75,31 @@ struct FusedArgs {
     int32_t* out_nnz;
     // dynamic shared memory carve-up
     int off_h1, off_h2, off_fk, off_fp, off_mixed, off_bits, off_wpre, off_acc;
+    int gen_cap;                        // power of two: (key, pos) pairs the general path can sort in shared memory
+                                        // (aliases the h1..fp regions)
     // global scratch for the general path: per CTA scratch_cap (key, pos) pairs
     void* scratch_key;
     void* scratch_pos;
     int scratch_cap;
+    // path statistics (nullable): [0] cells, [1] general: too many entries, [2] general: negatives below the
+    // cutoff, [3] general: crowded sub-bucket, [4] cells that needed zeros below the cutoff
+    unsigned long long* stats;
 };
+
+// warp-wide reductions: one REDUX instruction for 32-bit operands, shuffles for 64-bit keys
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint64_t warp_min(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = tmin(v, (uint64_t)__shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = tmax(v, (uint64_t)__shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 template <int NT>
 __device__ __forceinline__ int block_excl_scan_n(int v, int* s_warp, int& total) {
@@ -141,6 +161,65 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
     }
 }
 
+// One table entry j applied with multiplier mval (the body of scatter_packed, for the queued path).
+template <bool ACC64>
+__device__ __forceinline__ void apply_entry(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
+                                            uint32_t* __restrict__ acc_hi, uint32_t j, unsigned mval) {
+    if (ACC64) {
+        if (t.tent != nullptr) {
+            const unsigned long long ent = __ldg(t.tent + j);
+            const uint32_t r = (uint32_t)(ent & 0xFFFFull);
+            const long long w = ((long long)ent) >> 16;
+            const unsigned long long c = (unsigned long long)(w * (long long)mval);
+            const uint32_t lo = (uint32_t)c;
+            uint32_t hi = (uint32_t)(c >> 32);
+            const uint32_t old = atomicAdd(&acc_lo[r], lo);
+            hi += (old + lo < old) ? 1u : 0u;
+            if (hi) atomicAdd(&acc_hi[r], hi);
+        } else {
+            const uint32_t r = __ldg(t.tacc16 + j);
+            const uint32_t old = atomicAdd(&acc_lo[r], mval);
+            if (old + mval < old) atomicAdd(&acc_hi[r], 1u);
+        }
+    } else {
+        atomicAdd(&acc_lo[__ldg(t.tacc16 + j)], mval);
+    }
+}
+
+// Bucket-ordered storage of (key, pos): one 64-bit word when the key is 32-bit (single load + one compare in the
+// rank loop), two arrays otherwise.
+template <typename KeyT, typename PosT>
+struct BucketStore {
+    static constexpr bool packed = sizeof(KeyT) == 4;
+    static constexpr int key_bytes = packed ? 8 : (int)sizeof(KeyT);
+    unsigned long long* kp;   // packed
+    KeyT* k;                  // unpacked
+    PosT* p;
+    __device__ __forceinline__ void put(uint32_t at, KeyT key, PosT pos) const {
+        if (packed) kp[at] = ((unsigned long long)key << 32) | (unsigned long long)(uint32_t)pos;
+        else { k[at] = key; p[at] = pos; }
+    }
+    // 1 when the stored pair at `at` sorts strictly before (key, pos)
+    __device__ __forceinline__ uint32_t before(uint32_t at, KeyT key, PosT pos, unsigned long long mine) const {
+        if (packed) return kp[at] < mine ? 1u : 0u;
+        const KeyT ko = k[at];
+        return (ko < key || (ko == key && p[at] < pos)) ? 1u : 0u;
+    }
+};
+
+constexpr int kQ = kCapF / kFWarps;     // per-warp scatter queue (items): 256
+
+// Drain a warp's queue of (table entry, multiplier) items with all 32 lanes busy.
+template <bool ACC64>
+__device__ __forceinline__ void flush_queue(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
+                                            uint32_t* __restrict__ acc_hi, const uint32_t* __restrict__ qj,
+                                            const uint16_t* __restrict__ qm, int qn) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < qn; i += 32) apply_entry<ACC64>(t, acc_lo, acc_hi, qj[i], (unsigned)qm[i]);
+    __syncwarp();
+}
+
 template <bool ACC64, int NT>
 __device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
                                                   uint32_t* __restrict__ acc_hi, double* __restrict__ out) {
@@ -169,12 +248,23 @@ __device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_
 // ---- general path: all explicit entries of the cell into global scratch, bitonic sort, scatter --------------
 template <typename ValT, typename PosT, int IN, bool ACC64>
 __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s_bits, uint32_t* s_wpre,
-                             uint32_t* acc_lo, uint32_t* acc_hi, int* s_cnt, int* s_scan) {
+                             uint32_t* acc_lo, uint32_t* acc_hi, int* s_cnt, int* s_scan, unsigned char* smem) {
     using KT = KeyOf<ValT>;
     using KeyT = typename KT::type;
     const int tid = threadIdx.x, lane = tid & 31;
-    KeyT* lk = reinterpret_cast<KeyT*>(a.scratch_key) + (size_t)blockIdx.x * a.scratch_cap;
-    PosT* lp = reinterpret_cast<PosT*>(a.scratch_pos) + (size_t)blockIdx.x * a.scratch_cap;
+    // upper bound of the explicit entries: the row length.  Short rows are sorted in shared memory (the storage of
+    // the fast path's histograms and bucket arrays), long ones in global scratch.
+    int64_t bound = a.n_genes;
+    if (IN == IN_CSR) bound = a.indptr[cell + 1] - a.indptr[cell];
+    KeyT* lk;
+    PosT* lp;
+    if (bound <= a.gen_cap) {
+        lk = reinterpret_cast<KeyT*>(smem + a.off_h1);
+        lp = reinterpret_cast<PosT*>(lk + a.gen_cap);
+    } else {
+        lk = reinterpret_cast<KeyT*>(a.scratch_key) + (size_t)blockIdx.x * a.scratch_cap;
+        lp = reinterpret_cast<PosT*>(a.scratch_pos) + (size_t)blockIdx.x * a.scratch_cap;
+    }
     if (tid < 2) s_cnt[tid] = 0;
     __syncthreads();
     int64_t count;
@@ -291,9 +381,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* const h1 = reinterpret_cast<uint32_t*>(smem + a.off_h1);      // [kNb1 + 1]
     uint32_t* const h2 = reinterpret_cast<uint32_t*>(smem + a.off_h2);      // [kCapF + 1]
-    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);              // [kCapF] bucket-ordered keys
-    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);              // [kCapF] bucket-ordered positions
+    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);              // [kCapF] bucket-ordered keys (or packed pairs)
+    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);              // [kCapF] bucket-ordered positions / queue
     KeyT* const rep = fk;                                                   // [kNb1] alias: dead before fk is written
+    BucketStore<KeyT, PosT> store;
+    store.kp = reinterpret_cast<unsigned long long*>(smem + a.off_fk);
+    store.k = fk;
+    store.p = fp;
     uint32_t* const mixed = reinterpret_cast<uint32_t*>(smem + a.off_mixed);  // [kNb1 / 32]
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem + a.off_bits);
     uint32_t* const s_wpre = reinterpret_cast<uint32_t*>(smem + a.off_wpre);
@@ -317,10 +411,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         PosT pos[kItems];
         int m_total;                      // explicit entries of the cell
         bool general = false;
+        int why = 1;                      // reason code for the general path (statistics only)
+        int nk = 0;                       // item slots in use (block-uniform): slots >= nk hold nothing
         if (IN == IN_CSR) {
             const int64_t begin = a.indptr[cell];
             const int64_t count = a.indptr[cell + 1] - begin;
             general = count > kCapF;
+            nk = ((int)count + kF - 1) / kF;
             if (!general) {
                 const ValT* __restrict__ vals = a.data + begin;
                 const int32_t* __restrict__ cols = a.indices + begin;
@@ -328,15 +425,21 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 int c[kItems];
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
-                    const int i = k * kF + tid;
-                    const bool in = i < (int)count;
-                    v[k] = in ? vals[i] : (ValT)0;
-                    c[k] = in ? cols[i] : 0;
+                    v[k] = (ValT)0; c[k] = 0;
+                    if (k < nk) {
+                        const int i = k * kF + tid;
+                        const bool in = i < (int)count;
+                        v[k] = in ? vals[i] : (ValT)0;
+                        c[k] = in ? cols[i] : 0;
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
-                    key[k] = KT::make(v[k]);
-                    pos[k] = (key[k] != KT::KEY_ZERO) ? (PosT)__ldg(a.inv_perm + c[k]) : (PosT)0;
+                    key[k] = KT::KEY_ZERO; pos[k] = (PosT)0;
+                    if (k < nk) {
+                        key[k] = KT::make(v[k]);
+                        if (key[k] != KT::KEY_ZERO) pos[k] = (PosT)__ldg(a.inv_perm + c[k]);
+                    }
                 }
             }
             m_total = 0;
@@ -366,6 +469,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             __syncthreads();
             m_total = s_cnt[0];
             general = m_total > kCapF;
+            nk = (m_total + kF - 1) / kF;
             if (!general) {
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
@@ -384,6 +488,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             KeyT kmin = KT::KEY_ZERO, kmax = 0;
 #pragma unroll
             for (int k = 0; k < kItems; ++k) {
+                if (k >= nk) continue;
                 c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
                 if (key[k] < KT::KEY_ZERO) {
                     ++c_pos;
@@ -391,13 +496,10 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     kmax = tmax(kmax, key[k]);
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                c_exp += __shfl_xor_sync(0xffffffffu, c_exp, o);
-                c_pos += __shfl_xor_sync(0xffffffffu, c_pos, o);
-                kmin = tmin(kmin, (KeyT)__shfl_xor_sync(0xffffffffu, kmin, o));
-                kmax = tmax(kmax, (KeyT)__shfl_xor_sync(0xffffffffu, kmax, o));
-            }
+            c_exp = warp_sum(c_exp);
+            c_pos = warp_sum(c_pos);
+            kmin = warp_min(kmin);
+            kmax = warp_max(kmax);
             if (lane == 0) {
                 s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
                 s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
@@ -408,19 +510,14 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             if (tid == 0) s_flag[0] = 0;
             __syncthreads();
             {
-                int e = s_red_i[0][lane & (kFWarps - 1)], p = s_red_i[1][lane & (kFWarps - 1)];
-                KeyT mn = s_red_k[0][lane & (kFWarps - 1)], mx = s_red_k[1][lane & (kFWarps - 1)];
-#pragma unroll
-                for (int o = kFWarps / 2; o > 0; o >>= 1) {
-                    e += __shfl_xor_sync(0xffffffffu, e, o);
-                    p += __shfl_xor_sync(0xffffffffu, p, o);
-                    mn = tmin(mn, (KeyT)__shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = tmax(mx, (KeyT)__shfl_xor_sync(0xffffffffu, mx, o));
-                }
+                const bool has = lane < kFWarps;
+                const int e = warp_sum(has ? s_red_i[0][lane] : 0), p = warp_sum(has ? s_red_i[1][lane] : 0);
+                const KeyT mn = warp_min(has ? s_red_k[0][lane] : (KeyT)KT::KEY_ZERO);
+                const KeyT mx = warp_max(has ? s_red_k[1][lane] : (KeyT)0);
                 m = e; n_gt = p; kmin = mn; kmax = mx;
             }
             const int n_zero = n_genes - m;
-            if (cutoff - n_gt - n_zero > 0) general = true;      // negatives rank below the cutoff: general path
+            if (cutoff - n_gt - n_zero > 0) { general = true; why = 2; }   // negatives rank below the cutoff
 
             if (!general && n_gt > 0) {
                 // ---------------- RANK: two-level bucket sort of the positives ------------------------------
@@ -433,7 +530,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
                     bin[k] = 0xFFFFFFFFu;
-                    if (key[k] < KT::KEY_ZERO) {
+                    if (k < nk && key[k] < KT::KEY_ZERO) {
                         bin[k] = (uint32_t)((key[k] - kmin) >> shift);
                         atomicAdd(&h1[bin[k]], 1u);
                         rep[bin[k]] = key[k];
@@ -443,7 +540,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 // S2: mixed bins; exclusive scan of bin counts; n_s = entries in bins that start below the cutoff
 #pragma unroll
                 for (int k = 0; k < kItems; ++k)
-                    if (bin[k] != 0xFFFFFFFFu && rep[bin[k]] != key[k])
+                    if (k < nk && bin[k] != 0xFFFFFFFFu && rep[bin[k]] != key[k])
                         atomicOr(&mixed[bin[k] >> 5], 1u << (bin[k] & 31));
                 {
                     constexpr int per = kNb1 / kF;
@@ -474,7 +571,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
                     sbs[k] = 0xFFFFFFFFu;
-                    if (bin[k] != 0xFFFFFFFFu) {
+                    if (k < nk && bin[k] != 0xFFFFFFFFu) {
                         const uint32_t base = h1[bin[k]];
                         if ((int)base < cutoff) {
                             const uint32_t c = h1[bin[k] + 1] - base;
@@ -493,6 +590,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 __syncthreads();
                 if (s_flag[0]) {
                     general = true;       // crowded sub-bucket (uniform decision: read after the barrier)
+                    why = 3;
                 } else {
                     // S5: exclusive scan of level-2 counts
                     {
@@ -513,30 +611,62 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     // S6: entries into sub-bucket order (sub-buckets starting at or beyond the cutoff are dropped)
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
-                        if (sbs[k] != 0xFFFFFFFFu) {
+                        if (k < nk && sbs[k] != 0xFFFFFFFFu) {
                             const uint32_t b2 = h2[sbs[k] >> 8];
-                            if ((int)b2 < cutoff) {
-                                fk[b2 + (sbs[k] & 255u)] = key[k];
-                                fp[b2 + (sbs[k] & 255u)] = pos[k];
-                            } else {
-                                sbs[k] = 0xFFFFFFFFu;
-                            }
+                            if ((int)b2 < cutoff) store.put(b2 + (sbs[k] & 255u), key[k], pos[k]);
+                            else sbs[k] = 0xFFFFFFFFu;
                         }
                     }
                     __syncthreads();
-                    // S7: exact rank inside the sub-bucket, then scatter
+                    // S7: exact rank inside the sub-bucket -> multiplier cutoff - rank (0 = not below the cutoff),
+                    //     and the gene's row of the regulon table
+                    uint32_t mv[kItems], tb[kItems], tc[kItems];
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
-                        if (sbs[k] != 0xFFFFFFFFu) {
+                        mv[k] = 0u; tb[k] = 0u; tc[k] = 0u;
+                        if (k < nk && sbs[k] != 0xFFFFFFFFu) {
                             const uint32_t sb = sbs[k] >> 8;
                             const uint32_t b = h2[sb], e = h2[sb + 1];
+                            const unsigned long long mine = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)pos[k];
                             uint32_t rank = b;
-                            for (uint32_t j = b; j < e; ++j) {
-                                const KeyT ko = fk[j];
-                                rank += (ko < key[k] || (ko == key[k] && fp[j] < pos[k])) ? 1u : 0u;
+                            for (uint32_t j = b; j < e; ++j) rank += store.before(j, key[k], pos[k], mine);
+                            if ((int)rank < cutoff) {
+                                mv[k] = (uint32_t)(cutoff - (int)rank);
+                                tb[k] = __ldg(a.tab.tptr + (unsigned)pos[k]);
+                                tc[k] = __ldg(a.tab.tptr + (unsigned)pos[k] + 1) - tb[k];
                             }
-                            if ((int)rank < cutoff)
-                                scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)pos[k], (unsigned)(cutoff - (int)rank));
+                        }
+                    }
+                    __syncthreads();      // h2 / fp are dead: their storage becomes the per-warp scatter queues
+                    // S8: scatter through a per-warp queue so that every lane applies table entries
+                    {
+                        uint32_t* const qj = h2 + warp * kQ;
+                        uint16_t* const qm = reinterpret_cast<uint16_t*>(fp) + warp * kQ;
+                        int mine_n = 0;
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) mine_n += (int)tc[k];
+                        int incl = mine_n;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += tt;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (total <= kQ) {
+                            int at = incl - mine_n;
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) {
+                                for (uint32_t i = 0; i < tc[k]; ++i) {
+                                    qj[at] = tb[k] + i;
+                                    qm[at] = (uint16_t)mv[k];
+                                    ++at;
+                                }
+                            }
+                            flush_queue<ACC64>(a.tab, acc_lo, acc_hi, qj, qm, total);
+                        } else {              // more table entries than the queue holds: apply them directly
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k)
+                                for (uint32_t i = 0; i < tc[k]; ++i) apply_entry<ACC64>(a.tab, acc_lo, acc_hi, tb[k] + i, mv[k]);
                         }
                     }
                 }
@@ -544,11 +674,12 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             if (!general && n_gt < cutoff) {
                 // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -------------------------
                 const int q_zero = cutoff - n_gt;
+                if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
                 for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
                 __syncthreads();
 #pragma unroll
                 for (int k = 0; k < kItems; ++k)
-                    if (key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
+                    if (k < nk && key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
                 __syncthreads();
                 const int per = (a.n_words + kF - 1) / kF;
                 const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
@@ -574,9 +705,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             }
             if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
         }
+        if (a.stats != nullptr && tid == 0) {
+            atomicAdd(a.stats + 0, 1ull);
+            if (general) atomicAdd(a.stats + why, 1ull);
+        }
         if (general) {
             __syncthreads();
-            general_cell<ValT, PosT, IN, ACC64>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan);
+            general_cell<ValT, PosT, IN, ACC64>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan, smem);
         }
         __syncthreads();
         write_aucs_packed<ACC64, kF>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);

@@ -201,6 +201,13 @@ class AUCellPlan:
     def __exit__(self, *exc):
         self.close()
 
+    def path_stats(self, reset: bool = True) -> dict:
+        """Code paths the fused kernel took since the last reset (see aucell_plan_path_stats)."""
+        buf = (ctypes.c_uint64 * 5)()
+        _native.check(self._lib.aucell_plan_path_stats(self._handle, buf, 1 if reset else 0))
+        keys = ("cells", "general_too_many_entries", "general_negatives", "general_crowded_bin", "cells_with_zeros")
+        return dict(zip(keys, [int(x) for x in buf]))
+
     # ------------------------------------------------------------------ host buffers (library streams chunks)
     def aucell_dense_host(self, values: np.ndarray, want_nnz: bool = False, chunk_cells: int = 0):
         v = np.ascontiguousarray(values, dtype=np.float32)
