@@ -1,0 +1,178 @@
+# -*- coding: utf-8 -*-
+"""
+File I/O of the ``pyscenic aucell`` command (mirrors reference ``src/pyscenic/cli/utils.py``):
+
+    load_exp_matrix   utils.py:114-157   csv / tsv (always); loom / h5ad when loompy / anndata are importable
+    load_signatures   utils.py:205-227   gmt, dat (pickle), yaml (regulon records written by this package)
+    save_matrix       utils.py:160-179   csv / tsv (loom when loompy is importable)
+
+Unlike the reference, ``load_exp_matrix(..., return_sparse=True)`` is honoured for AUCell: a loom / h5ad matrix is
+handed to the GPU as CSR without densifying.
+"""
+from __future__ import annotations
+
+import pickle
+from pathlib import PurePath
+from typing import Sequence
+
+import numpy as np
+import pandas as pd
+
+from ..genesig import GeneSignature, Regulon, openfile
+
+__all__ = ["load_exp_matrix", "load_signatures", "save_matrix", "suffixes_to_separator", "guess_separator"]
+
+ATTRIBUTE_NAME_CELL_IDENTIFIER = "CellID"
+ATTRIBUTE_NAME_GENE = "Gene"
+
+_MATRIX_SUFFIXES = (".csv", ".tsv", ".loom", ".h5ad")
+
+
+def suffixes_to_separator(extension) -> str:
+    if ".csv" in extension:
+        return ","
+    if ".tsv" in extension:
+        return "\t"
+    raise ValueError("cannot derive a column separator from suffixes {}".format(extension))
+
+
+def _known_matrix(extension) -> bool:
+    return any(s in extension for s in _MATRIX_SUFFIXES)
+
+
+def _load_loom(fname, return_sparse, attr_cell, attr_gene):
+    try:
+        import loompy as lp
+    except ImportError as e:  # pragma: no cover - optional dependency
+        raise ValueError("reading loom files needs the loompy package: {}".format(e))
+    with lp.connect(fname, mode="r", validate=False) as ds:
+        genes = ds.ra[attr_gene]
+        cells = ds.ca[attr_cell]
+        if return_sparse:
+            return ds.layers[""].sparse().T.tocsr(), genes, cells
+        return pd.DataFrame(ds[:, :], index=genes, columns=cells).T
+
+
+def _load_h5ad(fname, return_sparse):
+    try:
+        from anndata import read_h5ad
+    except ImportError as e:  # pragma: no cover - optional dependency
+        raise ValueError("reading h5ad files needs the anndata package: {}".format(e))
+    import scipy.sparse as sp
+
+    adata = read_h5ad(filename=fname, backed="r")
+    x = adata.X[:] if hasattr(adata.X, "__getitem__") else adata.X
+    if return_sparse:
+        return sp.csr_matrix(x), adata.var_names.values, adata.obs_names.values
+    dense = x.todense() if sp.issparse(x) else np.asarray(x)
+    return pd.DataFrame(np.asarray(dense), index=adata.obs_names.values, columns=adata.var_names.values)
+
+
+def load_exp_matrix(
+    fname: str,
+    transpose: bool = False,
+    return_sparse: bool = False,
+    attribute_name_cell_id: str = ATTRIBUTE_NAME_CELL_IDENTIFIER,
+    attribute_name_gene: str = ATTRIBUTE_NAME_GENE,
+):
+    """
+    Load an expression matrix (rows = cells x columns = genes).
+
+    :return: a DataFrame, or ``(csr_matrix, gene_names, cell_names)`` when ``return_sparse`` and the file is loom/h5ad.
+    """
+    extension = PurePath(fname).suffixes
+    if not _known_matrix(extension):
+        raise ValueError('Unknown file format "{}".'.format(fname))
+    if ".loom" in extension:
+        return _load_loom(fname, return_sparse, attribute_name_cell_id, attribute_name_gene)
+    if ".h5ad" in extension:
+        return _load_h5ad(fname, return_sparse)
+    df = pd.read_csv(fname, sep=suffixes_to_separator(extension), header=0, index_col=0)
+    return df.T if transpose else df
+
+
+def save_matrix(df: pd.DataFrame, fname: str, transpose: bool = False) -> None:
+    """Save a matrix (rows = cells x columns = regulons) as csv / tsv (or a single-layer loom)."""
+    extension = PurePath(fname).suffixes
+    if not _known_matrix(extension):
+        raise ValueError('Unknown file format "{}".'.format(fname))
+    if ".loom" in extension:
+        try:
+            import loompy as lp
+        except ImportError as e:  # pragma: no cover - optional dependency
+            raise ValueError("writing loom files needs the loompy package: {}".format(e))
+        lp.create(
+            filename=fname,
+            layers=df.T.values,
+            row_attrs={ATTRIBUTE_NAME_GENE: df.columns.values.astype("str")},
+            col_attrs={ATTRIBUTE_NAME_CELL_IDENTIFIER: df.index.values.astype("str")},
+        )
+        return
+    if ".h5ad" in extension:
+        raise ValueError("h5ad output needs an h5ad input; use csv/tsv/loom for a stand-alone AUC matrix")
+    (df.T if transpose else df).to_csv(fname, sep=suffixes_to_separator(extension))
+
+
+def guess_separator(fname: str) -> str:
+    """Field separator of a GMT-like file: the first of tab, ';', ',' that yields at least three columns on every
+    non-comment line."""
+    with openfile(fname, "r") as f:
+        lines = [ln.decode() if isinstance(ln, (bytes, bytearray)) else ln for ln in f.readlines()]
+    body = [ln for ln in lines if ln.strip() and not ln.strip().startswith("#")]
+    for sep in ("\t", ";", ","):
+        if body and min(len(ln.split(sep)) for ln in body) >= 3:
+            return sep
+    raise ValueError('Unknown file format "{}".'.format(fname))
+
+
+def _load_yaml(fname: str):
+    import yaml
+
+    with openfile(fname, "r") as f:
+        docs = yaml.safe_load(f)
+    out = []
+    for d in docs:
+        g2w = d["gene2weight"]
+        if "transcription_factor" in d:
+            out.append(Regulon(name=d["name"], gene2weight=g2w, transcription_factor=d["transcription_factor"],
+                               context=frozenset(d.get("context", ())), score=d.get("score", 0.0)))
+        else:
+            out.append(GeneSignature(name=d["name"], gene2weight=g2w))
+    return out
+
+
+def save_to_yaml(signatures: Sequence[GeneSignature], fname: str) -> None:
+    import yaml
+
+    docs = []
+    for s in signatures:
+        d = {"name": s.name, "gene2weight": {g: float(w) for g, w in s.gene2weight.items()}}
+        if isinstance(s, Regulon):
+            d.update(transcription_factor=s.transcription_factor, context=sorted(s.context), score=float(s.score))
+        docs.append(d)
+    with openfile(fname, "w") as f:
+        yaml.safe_dump(docs, f)
+
+
+def load_signatures(fname: str) -> Sequence[GeneSignature]:
+    """
+    Load gene signatures: GMT, DAT (pickled list of signatures) or YAML.
+
+    The reference additionally turns a cisTarget motif-enrichment table (csv/tsv) into regulons via
+    ``pyscenic.transform.df2regulons``; that belongs to the ``ctx`` step and is not part of this package.
+    """
+    extension = PurePath(fname).suffixes
+    if ".csv" in extension or ".tsv" in extension:
+        raise ValueError(
+            'Unknown file format "{}": motif-enrichment tables must be converted to regulons by `pyscenic ctx` '
+            "tooling first (gmt, dat and yaml signatures are supported).".format(fname)
+        )
+    if ".yaml" in extension or ".yml" in extension:
+        return _load_yaml(fname)
+    if ".gmt" in extension:
+        sep = guess_separator(fname)
+        return GeneSignature.from_gmt(fname, field_separator=sep, gene_separator=sep)
+    if ".dat" in extension:
+        with openfile(fname, "rb") as f:
+            return pickle.load(f)
+    raise ValueError('Unknown file format "{}".'.format(fname))

@@ -1,0 +1,104 @@
+# -*- coding: utf-8 -*-
+"""`pyscenic aucell` command: argument surface and file I/O (CPU), end-to-end run against the oracle (GPU)."""
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import aucell_oracle as O
+from pyscenic_b200.cli import pyscenic as cli
+from pyscenic_b200.cli.utils import (guess_separator, load_exp_matrix, load_signatures, save_matrix, save_to_yaml)
+from pyscenic_b200.genesig import GeneSignature, Regulon
+
+
+def _write_inputs(tmp_path, n_cells=40, n_genes=300, seed=0):
+    rs = np.random.RandomState(seed)
+    X = rs.poisson(0.6, size=(n_cells, n_genes)).astype(np.float64)
+    df = pd.DataFrame(X, index=["cell%d" % i for i in range(n_cells)], columns=["g%d" % j for j in range(n_genes)])
+    expr = str(tmp_path / "expr.csv")
+    df.to_csv(expr)
+    sigs = [GeneSignature("sig%d" % k, ["g%d" % g for g in rs.choice(n_genes, 30, replace=False)]) for k in range(6)]
+    gmt = str(tmp_path / "sigs.gmt")
+    GeneSignature.to_gmt(gmt, sigs, field_separator="\t", gene_separator="\t")
+    return df, sigs, expr, gmt
+
+
+def test_parser_has_the_reference_flag_surface(tmp_path):
+    df, sigs, expr, gmt = _write_inputs(tmp_path)
+    p = cli.create_argument_parser()
+    a = p.parse_args(["aucell", expr, gmt])
+    # defaults of the reference (cli/pyscenic.py:340-360, 650-708): unweighted, thr 0.05, seed None, stdout
+    assert a.auc_threshold == 0.05 and a.weights is None and a.seed is None and a.transpose is None
+    import sys
+
+    assert a.output is sys.stdout and a.rank_threshold == 5000 and a.nes_threshold == 3.0
+    assert a.cell_id_attribute == "CellID" and a.gene_attribute == "Gene" and a.sparse is False
+    assert a.func is cli.aucell_command
+    a = p.parse_args(["aucell", expr, gmt, "-o", str(tmp_path / "o.csv"), "-t", "-w", "--num_workers", "3", "--seed",
+                      "7", "--auc_threshold", "0.1", "--sparse"])
+    assert a.transpose == "yes" and a.weights == "yes" and a.num_workers == 3 and a.seed == 7 and a.sparse is True
+    # @args file support
+    argsfile = tmp_path / "args.txt"
+    argsfile.write_text("aucell\n%s\n%s\n--seed\n5\n" % (expr, gmt))
+    assert p.parse_args(["@" + str(argsfile)]).seed == 5
+
+
+def test_matrix_and_signature_io(tmp_path):
+    df, sigs, expr, gmt = _write_inputs(tmp_path)
+    back = load_exp_matrix(expr)
+    assert back.shape == df.shape and list(back.columns) == list(df.columns) and np.array_equal(back.values, df.values)
+    df.T.to_csv(str(tmp_path / "t.tsv"), sep="\t")
+    assert np.array_equal(load_exp_matrix(str(tmp_path / "t.tsv"), transpose=True).values, df.values)
+    with pytest.raises(ValueError):
+        load_exp_matrix(str(tmp_path / "expr.parquet"))
+    assert guess_separator(gmt) == "\t"
+    got = load_signatures(gmt)
+    assert [s.name for s in got] == [s.name for s in sigs] and set(got[0].genes) == set(sigs[0].genes)
+    dat = str(tmp_path / "sigs.dat")
+    pickle.dump(sigs, open(dat, "wb"))
+    assert load_signatures(dat) == sigs
+    regs = [Regulon("TF1(+)", {"g1": 0.5, "g2": 2.0}, transcription_factor="TF1", context=frozenset(["activating"]))]
+    yml = str(tmp_path / "regs.yaml")
+    save_to_yaml(regs + sigs[:1], yml)
+    back = load_signatures(yml)
+    assert isinstance(back[0], Regulon) and back[0]["g2"] == 2.0 and back[0].transcription_factor == "TF1"
+    assert back[1] == sigs[0]
+    with pytest.raises(ValueError):
+        load_signatures(str(tmp_path / "motifs.csv"))
+    with pytest.raises(ValueError):
+        load_signatures(str(tmp_path / "x.json"))
+    out = str(tmp_path / "m.tsv")
+    save_matrix(df.iloc[:3, :4], out, transpose=True)
+    assert pd.read_csv(out, sep="\t", index_col=0).shape == (4, 3)
+    with pytest.raises(ValueError):
+        save_matrix(df, str(tmp_path / "m.xlsx"))
+
+
+def test_unknown_format_exits_with_status_1(tmp_path):
+    df, sigs, expr, gmt = _write_inputs(tmp_path)
+    bad = tmp_path / "expr.parquet"
+    bad.write_text("x")
+    with pytest.raises(SystemExit) as e:
+        cli.main(["aucell", str(bad), gmt])
+    assert e.value.code == 1
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_matches_oracle(tmp_path):
+    df, sigs, expr, gmt = _write_inputs(tmp_path, n_cells=64, n_genes=500)
+    out = str(tmp_path / "auc.csv")
+    cli.main(["aucell", expr, gmt, "-o", out, "--seed", "42", "--auc_threshold", "0.1"])
+    got = pd.read_csv(out, index_col=0)
+    want = O.aucell(df, sigs, auc_threshold=0.1, noweights=True, seed=42, num_workers=2)
+    assert list(got.index) == list(want.index) and list(got.columns) == list(want.columns)
+    assert np.allclose(got.values, want.values, rtol=1e-12, atol=0)     # csv text round trip of exact values
+    # transposed input and output, weighted flag, two shards on the same GPU
+    df.T.to_csv(str(tmp_path / "t.csv"))
+    out2 = str(tmp_path / "auc_t.tsv")
+    cli.main(["aucell", str(tmp_path / "t.csv"), gmt, "-t", "-w", "-o", out2, "--seed", "42", "--auc_threshold", "0.1",
+              "--devices", "0,0"])
+    got2 = pd.read_csv(out2, sep="\t", index_col=0)
+    assert got2.shape == (len(sigs), df.shape[0])
+    assert np.allclose(got2.T.values, want.values, rtol=1e-12, atol=0)
