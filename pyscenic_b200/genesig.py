@@ -48,6 +48,10 @@ def _convert(genes) -> Mapping:
     return MappingProxyType(d)
 
 
+def _rebuild(cls, fields):
+    return cls(**fields)
+
+
 class GeneSignature:
     """A named gene set with one weight per gene (immutable)."""
 
@@ -115,6 +119,10 @@ class GeneSignature:
 
     def _fields(self) -> dict:
         return {"name": self._name, "gene2weight": dict(self._gene2weight)}
+
+    def __reduce__(self):
+        # pickling (the reference's .dat signature files, cli/utils.py:223-225)
+        return (_rebuild, (type(self), self._fields()))
 
     # ------------------------------------------------------------------ derivation
     def copy(self, **kwargs) -> "GeneSignature":
