@@ -364,7 +364,8 @@ def run_ours(args, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload)
+                t = json.load(open(tp)).get(args.workload)
+                traffic = None if t is None else float(t["dram_bytes_per_cell"]) * n_cells   # per launch, like achieved
             except Exception:
                 traffic = None
         line = {
@@ -380,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "aucell_cell_kernel<%s>" % ("csr" if w["kind"] == "csr" else "dense"),
+                         "kernel": "aucell_fused_kernel<%s>" % ("csr" if w["kind"] == "csr" else "dense"),
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "bytes_per_cell": alg_bytes / n_cells},
             "cpu_baseline": cpu_baseline,
