@@ -213,15 +213,31 @@ int run_rank(const aucell_plan* p, const ValT* dense, int64_t row_stride, const 
 }
 
 // ---- fused AUCell kernel ------------------------------------------------------------------------------------
+// resident CTAs per SM of a kernel (registers, shared memory, threads): the persistent grid is a multiple of it
+template <typename K>
+int resident_ctas(K kernel, int threads, int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
 template <typename ValT, typename PosT, int IN>
-int launch_fused(const aucell_plan* p, const FusedArgs<ValT>& a, int smem, int grid, cudaStream_t st) {
+int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st,
+                 int key_bytes) {
+    int grid = 0;
     if (p->acc64) {
         auto k = aucell_fused_kernel<ValT, PosT, IN, true>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
+        if (rc) return rc;
         k<<<grid, kF, smem, st>>>(a);
     } else {
         auto k = aucell_fused_kernel<ValT, PosT, IN, false>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
+        if (rc) return rc;
         k<<<grid, kF, smem, st>>>(a);
     }
     g_launches.fetch_add(1);
@@ -266,9 +282,6 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     const int smem = off;
     if (smem > p->smem_optin)
         return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
-    const int per_sm = std::max<int>(1, std::min<int64_t>(2, (228 * 1024) / (smem + 1024)));
-    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * per_sm);
-
     a.dense = dense; a.row_stride = row_stride;
     a.indptr = indptr; a.indices = indices; a.data = data;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
@@ -279,10 +292,8 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
-    int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
-    if (rc) return rc;
-    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, grid, st);
-    return launch_fused<ValT, uint32_t, IN>(p, a, smem, grid, st);
+    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
+    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes);
 }
 
 }  // namespace

@@ -403,6 +403,19 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
 
     for (int i = tid; i < 2 * a.tab.n_acc; i += kF) acc_lo[i] = 0u;
+    // epilogue constants of "my" regulon (thread r owns regulon r when there are at most kF regulons)
+    const bool own_reg = a.tab.n_regulons <= kF;
+    int my_first = -1, my_parts = 0;
+    double my_scale0 = 1.0, my_scale1 = 0.0, my_max_auc = 1.0;
+    if (own_reg && tid < a.tab.n_regulons) {
+        my_first = __ldg(a.tab.acc_first + tid);
+        if (my_first >= 0) {
+            my_parts = __ldg(a.tab.acc_parts + tid);
+            my_scale0 = __ldg(a.tab.acc_scale + my_first);
+            if (my_parts > 1) my_scale1 = __ldg(a.tab.acc_scale + my_first + 1);
+            my_max_auc = __ldg(a.tab.max_auc + tid);
+        }
+    }
     __syncthreads();
 
     for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
@@ -638,7 +651,8 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         }
                     }
                     __syncthreads();      // h2 / fp are dead: their storage becomes the per-warp scatter queues
-                    // S8: scatter through a per-warp queue so that every lane applies table entries
+                    // S8: scatter through a per-warp queue of (table entry, multiplier) items so that every lane
+                    //     applies table entries (rows of the table have different lengths)
                     {
                         uint32_t* const qj = h2 + warp * kQ;
                         uint16_t* const qm = reinterpret_cast<uint16_t*>(fp) + warp * kQ;
@@ -714,7 +728,32 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             general_cell<ValT, PosT, IN, ACC64>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan, smem);
         }
         __syncthreads();
-        write_aucs_packed<ACC64, kF>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);
+        if (own_reg) {
+            if (tid < a.tab.n_regulons) {
+                double res = 0.0;
+                if (my_first >= 0) {
+                    double sum;
+                    if (ACC64) {
+                        const long long v0 = (long long)(((unsigned long long)acc_hi[my_first] << 32) | acc_lo[my_first]);
+                        sum = (double)v0 * my_scale0;
+                        acc_hi[my_first] = 0u;
+                        if (my_parts > 1) {
+                            const long long v1 = (long long)(((unsigned long long)acc_hi[my_first + 1] << 32) | acc_lo[my_first + 1]);
+                            sum += (double)v1 * my_scale1;
+                            acc_hi[my_first + 1] = 0u;
+                            acc_lo[my_first + 1] = 0u;
+                        }
+                    } else {
+                        sum = (double)acc_lo[my_first];
+                    }
+                    acc_lo[my_first] = 0u;
+                    res = __ddiv_rn(sum, my_max_auc);
+                }
+                a.out_auc[cell * (int64_t)a.tab.n_regulons + tid] = res;
+            }
+        } else {
+            write_aucs_packed<ACC64, kF>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);
+        }
         __syncthreads();
     }
 }
