@@ -373,26 +373,52 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     if (a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
 }
 
+// ---- row access ---------------------------------------------------------------------------------------------
+template <typename ValT>
+struct RowView {
+    const ValT* vals;
+    const int32_t* cols;     // nullptr for dense rows (column == index)
+    int count;               // stored entries (CSR) or n_genes (dense)
+};
+
+// Visit every element of a row with all threads in lock step (uniform trip count, so `f` may use warp votes):
+// f(is_explicit, key, column).
+template <typename ValT, typename F>
+__device__ __forceinline__ void stream_row(const RowView<ValT>& row, F f) {
+    using KT = KeyOf<ValT>;
+    using KeyT = typename KT::type;
+    for (int base = 0; base < row.count; base += kF) {
+        const int i = base + (int)threadIdx.x;
+        KeyT key = KT::KEY_ZERO;
+        int col = 0;
+        if (i < row.count) {
+            key = KT::make(row.vals[i]);
+            col = row.cols ? row.cols[i] : i;
+        }
+        f(key != KT::KEY_ZERO, key, col);
+    }
+}
+
 // ---- the fused kernel ---------------------------------------------------------------------------------------
 template <typename ValT, typename PosT, int IN, bool ACC64>
 __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<ValT> a) {
     using KT = KeyOf<ValT>;
     using KeyT = typename KT::type;
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* const h1 = reinterpret_cast<uint32_t*>(smem + a.off_h1);      // [kNb1 + 1]
-    uint32_t* const h2 = reinterpret_cast<uint32_t*>(smem + a.off_h2);      // [kCapF + 1]
-    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);              // [kCapF] bucket-ordered keys (or packed pairs)
-    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);              // [kCapF] bucket-ordered positions / queue
-    KeyT* const rep = fk;                                                   // [kNb1] alias: dead before fk is written
-    BucketStore<KeyT, PosT> store;
-    store.kp = reinterpret_cast<unsigned long long*>(smem + a.off_fk);
-    store.k = fk;
-    store.p = fp;
-    uint32_t* const mixed = reinterpret_cast<uint32_t*>(smem + a.off_mixed);  // [kNb1 / 32]
+    uint32_t* const h1 = reinterpret_cast<uint32_t*>(smem + a.off_h1);      // [kNb1 + 1] level-1 counts / bases
+    uint32_t* const h2 = reinterpret_cast<uint32_t*>(smem + a.off_h2);      // [kCapF + 1] level-2 counts / bases
+    KeyT* const rep = reinterpret_cast<KeyT*>(smem + a.off_h2);             // [kNb1] alias of h2: one key per bin
+    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);              // staging keys / packed bucket store
+    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);              // staging positions / bucket store / queue
+    uint32_t* const mixed = reinterpret_cast<uint32_t*>(smem + a.off_mixed);  // [kNb1 / 32] bins with > 1 key
     uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem + a.off_bits);
     uint32_t* const s_wpre = reinterpret_cast<uint32_t*>(smem + a.off_wpre);
     uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem + a.off_acc);
     uint32_t* const acc_hi = acc_lo + a.tab.n_acc;
+    BucketStore<KeyT, PosT> store;
+    store.kp = reinterpret_cast<unsigned long long*>(smem + a.off_fk);
+    store.k = fk;
+    store.p = fp;
     __shared__ int s_scan[33];
     __shared__ int s_cnt[2];
     __shared__ int s_red_i[2][kFWarps];
@@ -419,21 +445,34 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     __syncthreads();
 
     for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
-        // ---------------- LOAD: explicit entries into registers ----------------------------------------------
-        KeyT key[kItems];
-        PosT pos[kItems];
-        int m_total;                      // explicit entries of the cell
-        bool general = false;
-        int why = 1;                      // reason code for the general path (statistics only)
-        int nk = 0;                       // item slots in use (block-uniform): slots >= nk hold nothing
+        RowView<ValT> row;
         if (IN == IN_CSR) {
             const int64_t begin = a.indptr[cell];
-            const int64_t count = a.indptr[cell + 1] - begin;
-            general = count > kCapF;
-            nk = ((int)count + kF - 1) / kF;
-            if (!general) {
-                const ValT* __restrict__ vals = a.data + begin;
-                const int32_t* __restrict__ cols = a.indices + begin;
+            row.vals = a.data + begin;
+            row.cols = a.indices + begin;
+            row.count = (int)(a.indptr[cell + 1] - begin);
+        } else {
+            row.vals = a.dense + cell * a.row_stride;
+            row.cols = nullptr;
+            row.count = n_genes;
+        }
+
+        // ---------------- LOAD ---------------------------------------------------------------------------------
+        // direct mode: every explicit entry of the cell sits in registers (kItems per thread).
+        // select mode (long or dense rows): the row is streamed from global memory / L2 for the statistics and the
+        // level-1 histogram, and only the entries of the bins that start below the cutoff are brought to registers.
+        KeyT key[kItems];
+        PosT pos[kItems];
+        int nk = 0;                       // item slots in use (block-uniform): slots >= nk hold nothing
+        bool direct;
+        bool general = false;
+        int why = 1;                      // reason code for the general path (statistics only)
+        int c_exp = 0, c_pos = 0;         // this thread's explicit / positive entries
+        KeyT kmin = KT::KEY_ZERO, kmax = 0;
+        if (IN == IN_CSR) {
+            direct = row.count <= kCapF;
+            if (direct) {
+                nk = (row.count + kF - 1) / kF;
                 ValT v[kItems];
                 int c[kItems];
 #pragma unroll
@@ -441,9 +480,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     v[k] = (ValT)0; c[k] = 0;
                     if (k < nk) {
                         const int i = k * kF + tid;
-                        const bool in = i < (int)count;
-                        v[k] = in ? vals[i] : (ValT)0;
-                        c[k] = in ? cols[i] : 0;
+                        if (i < row.count) { v[k] = row.vals[i]; c[k] = row.cols[i]; }
                     }
                 }
 #pragma unroll
@@ -455,128 +492,182 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     }
                 }
             }
-            m_total = 0;
         } else {
-            // dense row: compact the non-zero values through shared memory (fk/fp as staging), then to registers
+            // dense row: compact the non-zero values into the staging arrays while taking the statistics
             if (tid == 0) s_cnt[0] = 0;
             __syncthreads();
-            const ValT* __restrict__ row = a.dense + cell * a.row_stride;
-            for (int base = 0; base < n_genes; base += kF) {
-                const int g = base + tid;
-                KeyT kk = KT::KEY_ZERO;
-                if (g < n_genes) kk = KT::make(row[g]);
-                const bool pred = kk != KT::KEY_ZERO;
-                const unsigned mk = __ballot_sync(0xffffffffu, pred);
+            stream_row(row, [&](bool ex, KeyT kk, int col) {
+                if (ex) {
+                    ++c_exp;
+                    if (kk < KT::KEY_ZERO) { ++c_pos; kmin = tmin(kmin, kk); kmax = tmax(kmax, kk); }
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, ex);
                 if (mk) {
                     int wbase = 0;
                     const int leader = __ffs(mk) - 1;
                     if (lane == leader) wbase = atomicAdd(&s_cnt[0], __popc(mk));
                     wbase = __shfl_sync(0xffffffffu, wbase, leader);
                     const int idx = wbase + __popc(mk & lanemask_lt());
-                    if (pred && idx < kCapF) {
+                    if (ex && idx < kCapF) {
                         fk[idx] = kk;
-                        fp[idx] = (PosT)__ldg(a.inv_perm + g);
+                        fp[idx] = (PosT)__ldg(a.inv_perm + col);
                     }
                 }
-            }
+            });
             __syncthreads();
-            m_total = s_cnt[0];
-            general = m_total > kCapF;
-            nk = (m_total + kF - 1) / kF;
-            if (!general) {
+            const int m_total = s_cnt[0];
+            direct = m_total <= kCapF;
+            if (direct) {
+                nk = (m_total + kF - 1) / kF;
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
                     const int i = k * kF + tid;
-                    key[k] = (i < m_total) ? fk[i] : KT::KEY_ZERO;
-                    pos[k] = (i < m_total) ? fp[i] : (PosT)0;
+                    key[k] = (k < nk && i < m_total) ? fk[i] : KT::KEY_ZERO;
+                    pos[k] = (k < nk && i < m_total) ? fp[i] : (PosT)0;
                 }
             }
-            __syncthreads();              // staging is free again (rep / fk are rewritten below)
         }
-
-        int n_gt = 0, m = 0;
-        if (!general) {
-            // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------
-            int c_exp = 0, c_pos = 0;
-            KeyT kmin = KT::KEY_ZERO, kmax = 0;
-#pragma unroll
-            for (int k = 0; k < kItems; ++k) {
-                if (k >= nk) continue;
-                c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
-                if (key[k] < KT::KEY_ZERO) {
-                    ++c_pos;
-                    kmin = tmin(kmin, key[k]);
-                    kmax = tmax(kmax, key[k]);
-                }
-            }
-            c_exp = warp_sum(c_exp);
-            c_pos = warp_sum(c_pos);
-            kmin = warp_min(kmin);
-            kmax = warp_max(kmax);
-            if (lane == 0) {
-                s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
-                s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
-            }
-            // clear the level-1 histogram while we are at it
-            for (int b = tid; b <= kNb1; b += kF) h1[b] = 0u;
-            if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
-            if (tid == 0) s_flag[0] = 0;
-            __syncthreads();
-            {
-                const bool has = lane < kFWarps;
-                const int e = warp_sum(has ? s_red_i[0][lane] : 0), p = warp_sum(has ? s_red_i[1][lane] : 0);
-                const KeyT mn = warp_min(has ? s_red_k[0][lane] : (KeyT)KT::KEY_ZERO);
-                const KeyT mx = warp_max(has ? s_red_k[1][lane] : (KeyT)0);
-                m = e; n_gt = p; kmin = mn; kmax = mx;
-            }
-            const int n_zero = n_genes - m;
-            if (cutoff - n_gt - n_zero > 0) { general = true; why = 2; }   // negatives rank below the cutoff
-
-            if (!general && n_gt > 0) {
-                // ---------------- RANK: two-level bucket sort of the positives ------------------------------
-                const KeyT range = kmax - kmin;
-                int nbits = 0;
-                if (range) nbits = (sizeof(KeyT) == 8) ? 64 - __clzll((long long)range) : 32 - __clz((int)range);
-                const int shift = max(0, nbits - kNb1Log);
-                uint32_t bin[kItems];
-                // S1: level-1 histogram, one representative key per bin
+        // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------------
+        if (direct) {
+            if (IN == IN_CSR) {
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
-                    bin[k] = 0xFFFFFFFFu;
+                    if (k >= nk) continue;
+                    c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
+                    if (key[k] < KT::KEY_ZERO) {
+                        ++c_pos;
+                        kmin = tmin(kmin, key[k]);
+                        kmax = tmax(kmax, key[k]);
+                    }
+                }
+            }
+        } else if (IN == IN_CSR) {
+            stream_row(row, [&](bool ex, KeyT kk, int) {
+                if (ex) {
+                    ++c_exp;
+                    if (kk < KT::KEY_ZERO) { ++c_pos; kmin = tmin(kmin, kk); kmax = tmax(kmax, kk); }
+                }
+            });
+        }
+        c_exp = warp_sum(c_exp);
+        c_pos = warp_sum(c_pos);
+        kmin = warp_min(kmin);
+        kmax = warp_max(kmax);
+        if (lane == 0) {
+            s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
+            s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
+        }
+        for (int b = tid; b <= kNb1; b += kF) h1[b] = 0u;     // clear the level-1 histogram while we are at it
+        if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
+        if (tid == 0) { s_flag[0] = 0; s_cnt[1] = 0; }
+        __syncthreads();
+        int m, n_gt;
+        {
+            const bool has = lane < kFWarps;
+            m = warp_sum(has ? s_red_i[0][lane] : 0);
+            n_gt = warp_sum(has ? s_red_i[1][lane] : 0);
+            kmin = warp_min(has ? s_red_k[0][lane] : (KeyT)KT::KEY_ZERO);
+            kmax = warp_max(has ? s_red_k[1][lane] : (KeyT)0);
+        }
+        const int n_zero = n_genes - m;
+        if (cutoff - n_gt - n_zero > 0) { general = true; why = 2; }   // negatives rank below the cutoff
+
+        if (!general && n_gt > 0) {
+            // ---------------- RANK: two-level bucket sort of the positives ------------------------------------
+            const KeyT range = kmax - kmin;
+            int nbits = 0;
+            if (range) nbits = (sizeof(KeyT) == 8) ? 64 - __clzll((long long)range) : 32 - __clz((int)range);
+            const int shift = max(0, nbits - kNb1Log);
+            // S1: level-1 histogram, one representative key per bin
+            if (direct) {
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
                     if (k < nk && key[k] < KT::KEY_ZERO) {
-                        bin[k] = (uint32_t)((key[k] - kmin) >> shift);
-                        atomicAdd(&h1[bin[k]], 1u);
-                        rep[bin[k]] = key[k];
+                        const uint32_t b = (uint32_t)((key[k] - kmin) >> shift);
+                        atomicAdd(&h1[b], 1u);
+                        rep[b] = key[k];
                     }
                 }
+            } else {
+                stream_row(row, [&](bool ex, KeyT kk, int) {
+                    if (ex && kk < KT::KEY_ZERO) {
+                        const uint32_t b = (uint32_t)((kk - kmin) >> shift);
+                        atomicAdd(&h1[b], 1u);
+                        rep[b] = kk;
+                    }
+                });
+            }
+            __syncthreads();
+            // S2: bins holding more than one distinct key (direct mode; select mode does it while selecting);
+            //     exclusive scan of the bin counts; n_s = entries in the bins that start below the cutoff
+            if (direct) {
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    if (k < nk && key[k] < KT::KEY_ZERO) {
+                        const uint32_t b = (uint32_t)((key[k] - kmin) >> shift);
+                        if (rep[b] != key[k]) atomicOr(&mixed[b >> 5], 1u << (b & 31));
+                    }
+                }
+            }
+            {
+                constexpr int per = kNb1 / kF;
+                const int b0 = tid * per;
+                int cnt[per];
+                int local = 0;
+#pragma unroll
+                for (int j = 0; j < per; ++j) { cnt[j] = (int)h1[b0 + j]; local += cnt[j]; }
+                int total;
+                int run = block_excl_scan_n<kF>(local, s_scan, total);
+                if (tid == 0) s_flag[1] = n_gt;
                 __syncthreads();
-                // S2: mixed bins; exclusive scan of bin counts; n_s = entries in bins that start below the cutoff
 #pragma unroll
-                for (int k = 0; k < kItems; ++k)
-                    if (k < nk && bin[k] != 0xFFFFFFFFu && rep[bin[k]] != key[k])
-                        atomicOr(&mixed[bin[k] >> 5], 1u << (bin[k] & 31));
-                {
-                    constexpr int per = kNb1 / kF;
-                    const int b0 = tid * per;
-                    int cnt[per];
-                    int local = 0;
-#pragma unroll
-                    for (int j = 0; j < per; ++j) { cnt[j] = (int)h1[b0 + j]; local += cnt[j]; }
-                    int total;
-                    int run = block_excl_scan_n<kF>(local, s_scan, total);
-                    if (tid == 0) s_flag[1] = n_gt;
+                for (int j = 0; j < per; ++j) {
+                    h1[b0 + j] = (uint32_t)run;
+                    if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];
+                    run += cnt[j];
+                }
+                if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
+            }
+            __syncthreads();
+            const int n_s = s_flag[1];
+            if (!direct) {
+                // SELECT: bring the entries of the kept bins to registers (through the staging arrays)
+                if (n_s > kCapF) {
+                    general = true;           // even the selection does not fit: general path
+                } else {
+                    stream_row(row, [&](bool ex, KeyT kk, int col) {
+                        bool keep = false;
+                        if (ex && kk < KT::KEY_ZERO) {
+                            const uint32_t b = (uint32_t)((kk - kmin) >> shift);
+                            keep = (int)h1[b] < cutoff;
+                            if (keep && rep[b] != kk) atomicOr(&mixed[b >> 5], 1u << (b & 31));
+                        }
+                        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                        if (mk) {
+                            int wbase = 0;
+                            const int leader = __ffs(mk) - 1;
+                            if (lane == leader) wbase = atomicAdd(&s_cnt[1], __popc(mk));
+                            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                            if (keep) {
+                                const int idx = wbase + __popc(mk & lanemask_lt());
+                                fk[idx] = kk;
+                                fp[idx] = (PosT)__ldg(a.inv_perm + col);
+                            }
+                        }
+                    });
                     __syncthreads();
+                    nk = (n_s + kF - 1) / kF;
 #pragma unroll
-                    for (int j = 0; j < per; ++j) {
-                        h1[b0 + j] = (uint32_t)run;
-                        if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];
-                        run += cnt[j];
+                    for (int k = 0; k < kItems; ++k) {
+                        const int i = k * kF + tid;
+                        key[k] = (k < nk && i < n_s) ? fk[i] : KT::KEY_ZERO;
+                        pos[k] = (k < nk && i < n_s) ? fp[i] : (PosT)0;
                     }
-                    if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
                 }
-                __syncthreads();
-                const int n_s = s_flag[1];
-                // S3: clear level-2 histogram
+                __syncthreads();              // staging and rep are free again
+            }
+            if (!general) {
+                // S3: clear level-2 histogram (rep is dead: its last readers finished before the barriers above)
                 for (int b = tid; b <= n_s; b += kF) h2[b] = 0u;
                 __syncthreads();
                 // S4: level-2 histogram
@@ -584,12 +675,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 #pragma unroll
                 for (int k = 0; k < kItems; ++k) {
                     sbs[k] = 0xFFFFFFFFu;
-                    if (k < nk && bin[k] != 0xFFFFFFFFu) {
-                        const uint32_t base = h1[bin[k]];
+                    if (k < nk && key[k] < KT::KEY_ZERO) {
+                        const uint32_t bin = (uint32_t)((key[k] - kmin) >> shift);
+                        const uint32_t base = h1[bin];
                         if ((int)base < cutoff) {
-                            const uint32_t c = h1[bin[k] + 1] - base;
+                            const uint32_t c = h1[bin + 1] - base;
                             uint32_t sub = 0;
-                            if (!((mixed[bin[k] >> 5] >> (bin[k] & 31)) & 1u)) {
+                            if (!((mixed[bin >> 5] >> (bin & 31)) & 1u)) {
                                 sub = (uint32_t)(((unsigned long long)((unsigned)pos[k]) * c * a.inv_ng) >> 32);
                                 sub = min(sub, c - 1u);
                             }
@@ -685,40 +777,49 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     }
                 }
             }
-            if (!general && n_gt < cutoff) {
-                // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -------------------------
-                const int q_zero = cutoff - n_gt;
-                if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
-                for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
-                __syncthreads();
+        }
+        if (!general && n_gt < cutoff) {
+            // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -----------------------------
+            const int q_zero = cutoff - n_gt;
+            if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
+            for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
+            __syncthreads();
+            if (direct) {
 #pragma unroll
                 for (int k = 0; k < kItems; ++k)
                     if (k < nk && key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
-                __syncthreads();
-                const int per = (a.n_words + kF - 1) / kF;
-                const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
-                int local = 0;
-                for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
-                int total;
-                int run = block_excl_scan_n<kF>(local, s_scan, total);
-                for (int w = w0; w < w1; ++w) {
-                    s_wpre[w] = (uint32_t)run;
-                    run += __popc(s_bits[w]);
-                }
-                __syncthreads();
-                for (int p = tid; p < n_genes; p += kF) {
-                    const int w = p >> 5;
-                    const uint32_t bw = s_bits[w];
-                    const int z0 = (w << 5) - (int)s_wpre[w];
-                    if (z0 >= q_zero) break;
-                    if (!((bw >> (p & 31)) & 1u)) {
-                        const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                        if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+            } else {
+                stream_row(row, [&](bool ex, KeyT, int col) {
+                    if (ex) {
+                        const unsigned p = (unsigned)__ldg(a.inv_perm + col);
+                        atomicOr(&s_bits[p >> 5], 1u << (p & 31));
                     }
+                });
+            }
+            __syncthreads();
+            const int per = (a.n_words + kF - 1) / kF;
+            const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
+            int local = 0;
+            for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
+            int total;
+            int run = block_excl_scan_n<kF>(local, s_scan, total);
+            for (int w = w0; w < w1; ++w) {
+                s_wpre[w] = (uint32_t)run;
+                run += __popc(s_bits[w]);
+            }
+            __syncthreads();
+            for (int p = tid; p < n_genes; p += kF) {
+                const int w = p >> 5;
+                const uint32_t bw = s_bits[w];
+                const int z0 = (w << 5) - (int)s_wpre[w];
+                if (z0 >= q_zero) break;
+                if (!((bw >> (p & 31)) & 1u)) {
+                    const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
+                    if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
                 }
             }
-            if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
         }
+        if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
         if (a.stats != nullptr && tid == 0) {
             atomicAdd(a.stats + 0, 1ull);
             if (general) atomicAdd(a.stats + why, 1ull);

@@ -284,7 +284,11 @@ def test_fast_path_and_its_fallback(unweighted):
     X[3, 5] = np.inf
     X[4] = 0.0; X[4, idx[:400]] = 2.0; X[4, idx[400:]] = np.nextafter(np.float32(2.0), np.float32(3.0))  # 2 keys, 1 bin
     X[5] = 0.0; X[5, idx[:50]] = np.float32(1e-45)                            # denormals only, n_pos < cutoff
-    X[6] = np.abs(rs.randn(n_genes)).astype(np.float32) + 1.0                 # dense positive: list overflow
+    X[6] = np.abs(rs.randn(n_genes)).astype(np.float32) + 1.0                 # dense positive: select mode
+    X[7] = -np.abs(rs.randn(n_genes)).astype(np.float32)                      # select mode + zeros below the cutoff:
+    X[7, idx[:100]] = rs.rand(100).astype(np.float32) + 1; X[7, idx[100:]] = 0.0   # 100 pos, 800 zeros, 5100 neg
+    X[8] = rs.poisson(3.0, n_genes).astype(np.float32)                        # 95 % non-zero counts: long row, ties
+    X[9] = 7.0                                                                # one value everywhere
     reg = synth.make_regulons(rs, n_genes, 50, 10, 400, weighted=True)
     perm = np.random.RandomState(5).permutation(n_genes)
     want = oracle_auc(X, perm, reg, cutoff, unweighted)
