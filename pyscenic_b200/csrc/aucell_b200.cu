@@ -87,6 +87,14 @@ struct aucell_plan {
     double* d_acc_scale = nullptr;
     double* d_reg_max_auc = nullptr;
     unsigned long long* d_stats = nullptr;   // path statistics of the fused kernel (5 counters)
+    // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
+    struct HostSlot {
+        cudaStream_t st = nullptr;
+        char* buf = nullptr;       // one allocation: indptr | indices | values | auc | nnz
+        size_t bytes = 0;
+    };
+    mutable std::mutex host_mu;
+    mutable std::vector<HostSlot> host_slots;
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;
     mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
@@ -529,6 +537,10 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_acc_scale);
     cudaFree(p->d_reg_max_auc);
     for (auto& kv : p->scratch) cudaFree(kv.second.first);
+    for (auto& hs : p->host_slots) {
+        if (hs.st) { cudaStreamSynchronize(hs.st); cudaStreamDestroy(hs.st); }
+        cudaFree(hs.buf);
+    }
     delete p;
     return AUCELL_OK;
 }
@@ -613,22 +625,25 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
 // ---- host-buffer streaming pipeline ------------------------------------------------------------------
 namespace {
 
-struct Slot {
-    cudaStream_t st = nullptr;
-    int64_t* d_indptr = nullptr;
-    int32_t* d_indices = nullptr;
-    float* d_vals = nullptr;   // CSR data or dense rows
-    double* d_auc = nullptr;
-    int32_t* d_nnz = nullptr;
-};
+constexpr int kHostSlots = 4;
 
-void free_slots(std::vector<Slot>& s) {
-    for (auto& x : s) {
-        if (x.st) cudaStreamSynchronize(x.st);
-        cudaFree(x.d_indptr); cudaFree(x.d_indices); cudaFree(x.d_vals); cudaFree(x.d_auc); cudaFree(x.d_nnz);
-        if (x.st) cudaStreamDestroy(x.st);
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Make sure the plan owns kHostSlots staging buffers of at least `bytes` each (and their streams).
+int ensure_host_slots(const aucell_plan* p, size_t bytes) {
+    if (p->host_slots.empty()) p->host_slots.resize(kHostSlots);
+    for (auto& hs : p->host_slots) {
+        if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
+        if (hs.bytes < bytes) {
+            CK(cudaStreamSynchronize(hs.st));
+            cudaFree(hs.buf);
+            hs.buf = nullptr;
+            hs.bytes = 0;
+            CK(cudaMalloc(&hs.buf, bytes));
+            hs.bytes = bytes;
+        }
     }
-    s.clear();
+    return AUCELL_OK;
 }
 
 }  // namespace
@@ -643,63 +658,57 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     if (!h_indptr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    std::lock_guard<std::mutex> host_lock(p->host_mu);
     const int64_t R = p->n_regulons;
     const int64_t total_nnz = h_indptr[n_cells] - h_indptr[0];
     if (total_nnz > 0 && (!h_indices || !h_data)) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     if (chunk_cells <= 0) {
-        // ~192 MB of (index, value) pairs per chunk
+        // ~128 MB of (index, value) pairs per chunk
         const double per_cell = std::max<double>(1.0, (double)total_nnz / (double)n_cells);
-        chunk_cells = (int64_t)std::max<double>(1024.0, (192.0 * 1024 * 1024) / (8.0 * per_cell));
+        chunk_cells = (int64_t)std::max<double>(1024.0, (128.0 * 1024 * 1024) / (8.0 * per_cell));
     }
     chunk_cells = std::min(chunk_cells, n_cells);
-    // chunk nnz upper bound
     int64_t max_nnz = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells) {
-        int64_t c1 = std::min(n_cells, c0 + chunk_cells);
+        const int64_t c1 = std::min(n_cells, c0 + chunk_cells);
         max_nnz = std::max(max_nnz, h_indptr[c1] - h_indptr[c0]);
     }
-    const int n_slots = (int)std::min<int64_t>(3, (n_cells + chunk_cells - 1) / chunk_cells);
-    std::vector<Slot> slots(n_slots);
-    int rc = AUCELL_OK;
-#define HCK(call)                                                      \
-    do {                                                               \
-        cudaError_t e_ = (call);                                       \
-        if (e_ != cudaSuccess) {                                       \
-            rc = fail_cuda(e_, #call, __LINE__);                       \
-            free_slots(slots);                                         \
-            return rc;                                                 \
-        }                                                              \
-    } while (0)
-    for (auto& s : slots) {
-        HCK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        HCK(cudaMalloc(&s.d_indptr, sizeof(int64_t) * (chunk_cells + 1)));
-        HCK(cudaMalloc(&s.d_indices, sizeof(int32_t) * std::max<int64_t>(max_nnz, 1)));
-        HCK(cudaMalloc(&s.d_vals, sizeof(float) * std::max<int64_t>(max_nnz, 1)));
-        HCK(cudaMalloc(&s.d_auc, sizeof(double) * chunk_cells * R));
-        if (h_out_nnz) HCK(cudaMalloc(&s.d_nnz, sizeof(int32_t) * chunk_cells));
-    }
+    const size_t o_indptr = 0;
+    const size_t o_indices = align256(o_indptr + sizeof(int64_t) * (chunk_cells + 1));
+    const size_t o_vals = align256(o_indices + sizeof(int32_t) * std::max<int64_t>(max_nnz, 1));
+    const size_t o_auc = align256(o_vals + sizeof(float) * std::max<int64_t>(max_nnz, 1));
+    const size_t o_nnz = align256(o_auc + sizeof(double) * chunk_cells * R);
+    const size_t bytes = align256(o_nnz + sizeof(int32_t) * chunk_cells);
+    int rc = ensure_host_slots(p, bytes);
+    if (rc) return rc;
     int k = 0;
-    for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % n_slots) {
-        Slot& s = slots[k];
+    for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
+        const aucell_plan::HostSlot& s = p->host_slots[k];
+        int64_t* d_indptr = reinterpret_cast<int64_t*>(s.buf + o_indptr);
+        int32_t* d_indices = reinterpret_cast<int32_t*>(s.buf + o_indices);
+        float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
+        double* d_auc = reinterpret_cast<double*>(s.buf + o_auc);
+        int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
         const int64_t c1 = std::min(n_cells, c0 + chunk_cells);
         const int64_t nc = c1 - c0;
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
-        // stream order on s.st protects the slot's buffers from the previous chunk that used it
-        HCK(cudaMemcpyAsync(s.d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
+        // stream order on the slot's stream protects its buffers from the previous chunk that used them
+        CK(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
         if (ne > 0) {
-            HCK(cudaMemcpyAsync(s.d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
-            HCK(cudaMemcpyAsync(s.d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
+            CK(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+            CK(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
         }
         // the kernel indexes indices/data with the absolute offsets of h_indptr: shift the bases
-        rc = aucell_csr_f32(p, s.d_indptr, s.d_indices - e0, s.d_vals - e0, nc, s.d_auc, s.d_nnz, s.st);
-        if (rc) { free_slots(slots); return rc; }
-        HCK(cudaMemcpyAsync(h_out_auc + c0 * R, s.d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
-        if (h_out_nnz)
-            HCK(cudaMemcpyAsync(h_out_nnz + c0, s.d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        rc = aucell_csr_f32(p, d_indptr, d_indices - e0, d_vals - e0, nc, d_auc, d_nnz, s.st);
+        if (rc) break;
+        CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+        if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
-    for (auto& s : slots) HCK(cudaStreamSynchronize(s.st));
-    free_slots(slots);
-    return AUCELL_OK;
+    for (auto& s : p->host_slots) {
+        cudaError_t e = cudaStreamSynchronize(s.st);
+        if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+    }
+    return rc;
 }
 
 int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n_cells, int64_t row_stride,
@@ -711,35 +720,35 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
     if (!h_expr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    std::lock_guard<std::mutex> host_lock(p->host_mu);
     const int64_t R = p->n_regulons;
     if (chunk_cells <= 0)
-        chunk_cells = std::max<int64_t>(256, (int64_t)(192.0 * 1024 * 1024 / (4.0 * (double)row_stride)));
+        chunk_cells = std::max<int64_t>(256, (int64_t)(128.0 * 1024 * 1024 / (4.0 * (double)row_stride)));
     chunk_cells = std::min(chunk_cells, n_cells);
-    const int n_slots = (int)std::min<int64_t>(3, (n_cells + chunk_cells - 1) / chunk_cells);
-    std::vector<Slot> slots(n_slots);
-    int rc = AUCELL_OK;
-    for (auto& s : slots) {
-        HCK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        HCK(cudaMalloc(&s.d_vals, sizeof(float) * chunk_cells * row_stride));
-        HCK(cudaMalloc(&s.d_auc, sizeof(double) * chunk_cells * R));
-        if (h_out_nnz) HCK(cudaMalloc(&s.d_nnz, sizeof(int32_t) * chunk_cells));
-    }
+    const size_t o_vals = 0;
+    const size_t o_auc = align256(o_vals + sizeof(float) * chunk_cells * row_stride);
+    const size_t o_nnz = align256(o_auc + sizeof(double) * chunk_cells * R);
+    const size_t bytes = align256(o_nnz + sizeof(int32_t) * chunk_cells);
+    int rc = ensure_host_slots(p, bytes);
+    if (rc) return rc;
     int k = 0;
-    for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % n_slots) {
-        Slot& s = slots[k];
+    for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
+        const aucell_plan::HostSlot& s = p->host_slots[k];
+        float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
+        double* d_auc = reinterpret_cast<double*>(s.buf + o_auc);
+        int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
         const int64_t nc = std::min(n_cells, c0 + chunk_cells) - c0;
-        HCK(cudaMemcpyAsync(s.d_vals, h_expr + c0 * row_stride, sizeof(float) * nc * row_stride,
-                            cudaMemcpyHostToDevice, s.st));
-        rc = aucell_dense_f32(p, s.d_vals, nc, row_stride, s.d_auc, s.d_nnz, s.st);
-        if (rc) { free_slots(slots); return rc; }
-        HCK(cudaMemcpyAsync(h_out_auc + c0 * R, s.d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
-        if (h_out_nnz)
-            HCK(cudaMemcpyAsync(h_out_nnz + c0, s.d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(d_vals, h_expr + c0 * row_stride, sizeof(float) * nc * row_stride, cudaMemcpyHostToDevice, s.st));
+        rc = aucell_dense_f32(p, d_vals, nc, row_stride, d_auc, d_nnz, s.st);
+        if (rc) break;
+        CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+        if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
-    for (auto& s : slots) HCK(cudaStreamSynchronize(s.st));
-    free_slots(slots);
-    return AUCELL_OK;
+    for (auto& s : p->host_slots) {
+        cudaError_t e = cudaStreamSynchronize(s.st);
+        if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+    }
+    return rc;
 }
-#undef HCK
 
 }  // extern "C"
