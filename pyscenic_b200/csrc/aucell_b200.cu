@@ -606,15 +606,16 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = align16(p->n_acc * 8);
     if (smem > p->smem_optin) return fail(AUCELL_ERR_UNSUPPORTED, "too many regulons for the shared-memory accumulators");
-    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * 8);
     GeneTableDev reg = tab_of(p);
     if (p->acc64) {
         auto k = aucell_from_rankings_kernel<true>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
         k<<<grid, kF, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, d_out_auc);
     } else {
         auto k = aucell_from_rankings_kernel<false>;
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
         k<<<grid, kF, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, d_out_auc);
     }
     g_launches.fetch_add(1);

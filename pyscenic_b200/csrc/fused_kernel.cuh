@@ -873,7 +873,24 @@ __global__ void __launch_bounds__(kF) aucell_from_rankings_kernel(const uint32_t
     __syncthreads();
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const uint32_t* row = rnk + cell * row_stride;
-        for (int j = tid; j < n_genes; j += kF) {
+        // 128-bit loads over the 16-byte aligned interior of the row, scalar loads for the ragged edges
+        const int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(row) & 15u)) & 15u) >> 2);
+        const int h = min(head, n_genes);
+        const int n4 = (n_genes - h) >> 2;
+        if (tid < h) {
+            const uint32_t r = row[tid];
+            if (r < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)tid, (uint32_t)cutoff - r);
+        }
+        const uint4* row4 = reinterpret_cast<const uint4*>(row + h);
+        for (int q = tid; q < n4; q += kF) {
+            const uint4 v = __ldg(row4 + q);
+            const int j = h + (q << 2);
+            if (v.x < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)j, (uint32_t)cutoff - v.x);
+            if (v.y < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 1), (uint32_t)cutoff - v.y);
+            if (v.z < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 2), (uint32_t)cutoff - v.z);
+            if (v.w < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 3), (uint32_t)cutoff - v.w);
+        }
+        for (int j = h + (n4 << 2) + tid; j < n_genes; j += kF) {
             const uint32_t r = row[j];
             if (r < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)j, (uint32_t)cutoff - r);
         }
