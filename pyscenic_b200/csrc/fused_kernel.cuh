@@ -101,7 +101,8 @@ __device__ __forceinline__ uint64_t warp_max(uint64_t v) {
     return v;
 }
 
-template <int NT>
+// TRAILING_BARRIER = false: the caller guarantees a block barrier before s_warp is written again.
+template <int NT, bool TRAILING_BARRIER = true>
 __device__ __forceinline__ int block_excl_scan_n(int v, int* s_warp, int& total) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -127,7 +128,7 @@ __device__ __forceinline__ int block_excl_scan_n(int v, int* s_warp, int& total)
     __syncthreads();
     total = s_warp[32];
     const int res = s_warp[w] + incl - v;
-    __syncthreads();
+    if (TRAILING_BARRIER) __syncthreads();
     return res;
 }
 
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     store.k = fk;
     store.p = fp;
     __shared__ int s_scan[33];
+    __shared__ int s_scan2[33];
     __shared__ int s_cnt[2];
     __shared__ int s_red_i[2][kFWarps];
     __shared__ KeyT s_red_k[2][kFWarps];
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         }
         for (int b = tid; b <= kNb1; b += kF) h1[b] = 0u;     // clear the level-1 histogram while we are at it
         if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
-        if (tid == 0) { s_flag[0] = 0; s_cnt[1] = 0; }
+        if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0x7FFFFFFF; s_cnt[1] = 0; }
         __syncthreads();
         int m, n_gt;
         {
@@ -617,19 +619,17 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 #pragma unroll
                 for (int j = 0; j < per; ++j) { cnt[j] = (int)h1[b0 + j]; local += cnt[j]; }
                 int total;
-                int run = block_excl_scan_n<kF>(local, s_scan, total);
-                if (tid == 0) s_flag[1] = n_gt;
-                __syncthreads();
+                int run = block_excl_scan_n<kF, false>(local, s_scan, total);
 #pragma unroll
                 for (int j = 0; j < per; ++j) {
                     h1[b0 + j] = (uint32_t)run;
-                    if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];
+                    if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];   // at most one writer
                     run += cnt[j];
                 }
                 if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
             }
             __syncthreads();
-            const int n_s = s_flag[1];
+            const int n_s = min(s_flag[1], n_gt);      // sentinel when all positives rank below the cutoff
             if (!direct) {
                 // SELECT: bring the entries of the kept bins to registers (through the staging arrays)
                 if (n_s > kCapF) {
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         int local = 0;
                         for (int b = b0; b < b1; ++b) local += (int)h2[b];
                         int total;
-                        int run = block_excl_scan_n<kF>(local, s_scan, total);
+                        int run = block_excl_scan_n<kF, false>(local, s_scan2, total);
                         for (int b = b0; b < b1; ++b) {
                             const int c = (int)h2[b];
                             h2[b] = (uint32_t)run;
@@ -855,7 +855,8 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         } else {
             write_aucs_packed<ACC64, kF>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);
         }
-        __syncthreads();
+        // no barrier here: the epilogue only touches the accumulators, and every path of the next cell passes
+        // several block barriers before its first scatter
     }
 }
 
