@@ -108,13 +108,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- workload
-def make_regulon_tables(w, rs):
+def make_regulon_tables(w, rs, weighted=True):
     import synth
     from pyscenic_b200.plan import derive_rank_cutoff
 
-    reg = synth.make_regulons(rs, w["n_genes"], w["n_regulons"], 10, 400, weighted=True, repressors=True)
+    reg = synth.make_regulons(rs, w["n_genes"], w["n_regulons"], 10, 400, weighted=weighted, repressors=True)
     cutoff = derive_rank_cutoff(AUC_THRESHOLD, w["n_genes"])
-    tables = synth.regulon_tables_from_arrays(*reg, n_genes=w["n_genes"], rank_cutoff=cutoff)
+    tables = synth.regulon_tables_from_arrays(*reg, n_genes=w["n_genes"], rank_cutoff=cutoff, unweighted=not weighted)
     return reg, tables, cutoff
 
 
@@ -187,7 +187,7 @@ def run_reference(args, rank, world):
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     rs = np.random.RandomState(1234)
-    reg, tables, cutoff = make_regulon_tables(w, rs)
+    reg, tables, cutoff = make_regulon_tables(w, rs, not args.unweighted)
     n_sample = args.ref_cells
     from oracle import aucell_oracle as O
 
@@ -233,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     rs = np.random.RandomState(1234)                       # regulons identical on every rank
-    reg, tables, cutoff = make_regulon_tables(w, rs)
+    reg, tables, cutoff = make_regulon_tables(w, rs, not args.unweighted)
     perm = np.random.RandomState(SEED).permutation(w["n_genes"])
     plan = AUCellPlan(w["n_genes"], perm, tables, device=local_rank)
     n_cells, n_genes, R = w["n_cells"], w["n_genes"], w["n_regulons"]
@@ -374,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys -> u32 ranks, f64 AUC", "data": "synthetic",
             "config": {"workload": w["desc"], "cells_per_gpu": n_cells, "n_genes": n_genes, "n_regulons": R,
                        "nnz_per_cell": total_nnz / n_cells, "auc_threshold": AUC_THRESHOLD, "rank_cutoff": cutoff,
-                       "seed": SEED, "weighted": True,
+                       "seed": SEED, "weighted": not args.unweighted,
                        "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9)},
             "clocks": clocks,
             "e2e": e2e,
@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (debugging)")
     ap.add_argument("--ref-cells", type=int, default=2048, help="cells in the CPU reference sample")
+    ap.add_argument("--unweighted", action="store_true", help="unit gene weights (the CLI default of the reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -412,3 +412,41 @@ def test_enrichment_alias_matches_oracle():
     assert list(got.index.names) == ["Cell", "Regulon"] and list(got.columns) == ["AUC"]
     assert got.index.equals(want.index)
     assert np.array_equal(got["AUC"].values, want["AUC"].values)
+
+
+def test_config3_full_size_properties_and_spot_check():
+    """BASELINE.json configs[2] at FULL size (100k cells x 25k genes CSR, 500 regulons): size-independent properties
+    (determinism, sharding invariance, value range, permutation-invariance of the cell order) plus an oracle
+    spot-check of 192 cells drawn from the whole matrix."""
+    import torch
+
+    n_cells, n_genes = 100_000, 25_000
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1750, seed=21, device="cuda")
+    rs = np.random.RandomState(5)
+    reg = synth.make_regulons(rs, n_genes, 500, 10, 400, weighted=True, repressors=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(42).permutation(n_genes)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        a = plan.aucell_csr(indptr, indices, data)
+        b = plan.aucell_csr(indptr, indices, data)
+        assert torch.equal(a, b)                                        # deterministic
+        stats = plan.path_stats()
+        assert stats["cells"] == 2 * n_cells
+        # two halves computed separately == the whole (what cell sharding over GPUs relies on)
+        mid = 41_337
+        e_mid = int(indptr[mid])
+        lo = plan.aucell_csr(indptr[: mid + 1].contiguous(), indices[:e_mid].contiguous(), data[:e_mid].contiguous())
+        hi = plan.aucell_csr((indptr[mid:] - e_mid).contiguous(), indices[e_mid:].contiguous(), data[e_mid:].contiguous())
+        assert torch.equal(torch.cat([lo, hi]), a)
+        # the host-buffer entry point gives the same matrix
+        h = plan.aucell_csr_host(indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy())
+        assert np.array_equal(h, a.cpu().numpy())
+    av = a.cpu().numpy()
+    assert np.isfinite(av).all() and av.min() >= 0.0 and av.max() < 1.0
+    pick = np.random.RandomState(0).choice(n_cells, 192, replace=False)
+    ip = indptr.cpu().numpy()
+    ix, dv = indices.cpu().numpy(), data.cpu().numpy()
+    X = np.zeros((len(pick), n_genes), dtype=np.float32)
+    for r, c in enumerate(pick):
+        X[r, ix[ip[c]:ip[c + 1]]] = dv[ip[c]:ip[c + 1]]
+    assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))

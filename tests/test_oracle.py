@@ -207,3 +207,38 @@ def test_mismatch_gives_zero_column_and_warning(caplog):
         res = O.aucell(df.iloc[:20], [fake] + sigs[:3], seed=1, num_workers=1)
     assert (res["test"] == 0.0).all()
     assert "Less than 80% of the genes in test are present" in caplog.text
+
+
+# ------------------------------------------------------------------------------------------ property tests
+def test_property_rankings_and_aucs_hypothesis():
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    vals = st.one_of(st.integers(0, 4).map(float), st.sampled_from([np.nan, np.inf, -np.inf, -0.0, 1e-45, -2.5]))
+
+    @settings(max_examples=60, deadline=None)
+    @given(hnp.arrays(np.float64, hnp.array_shapes(min_dims=2, max_dims=2, min_side=1, max_side=12), elements=vals),
+           st.integers(0, 2**31 - 1))
+    def check(x, seed):
+        n = x.shape[1]
+        perm = O.permutation_from_seed(n, seed)
+        r_np = O.create_rankings_np(x, perm)
+        r_c = O.create_rankings_c(x, perm)
+        assert np.array_equal(r_np, r_c)
+        # every row is a permutation of 0..n-1 (the property the reference's own test pins)
+        assert np.array_equal(np.sort(r_np, axis=1), np.tile(np.arange(n, dtype=np.uint32), (x.shape[0], 1)))
+        # pandas agrees (float32 to keep denormals as given)
+        df = pd.DataFrame(x.astype(np.float32))
+        assert np.array_equal(O.create_rankings(df, seed=seed).values, O.create_rankings_c(x.astype(np.float32), perm))
+        # closed form == sequential form for unit weights, and 0 <= AUC < 1
+        if n >= 4:
+            cutoff = max(1, n // 2)
+            for row in r_np:
+                w = np.ones(n)
+                m = float((cutoff + 1) * w.sum())
+                a = O.weighted_auc1d_c(row, w, cutoff, m)
+                hit = row < cutoff
+                assert a == float((cutoff - row[hit].astype(np.int64)).sum()) / m
+                assert 0.0 <= a < 1.0
+
+    check()
