@@ -40,7 +40,7 @@ constexpr int kF = 512;                 // threads per CTA of the fused kernel
 constexpr int kFWarps = kF / 32;
 constexpr int kItems = 8;               // register-resident entries per thread
 constexpr int kCapF = kF * kItems;      // 4096 explicit entries per cell on the fast path
-constexpr int kNb1Log = 11;             // level-1 value bins
+constexpr int kNb1Log = 10;             // level-1 value bins
 constexpr int kNb1 = 1 << kNb1Log;
 constexpr int kMaxSub = 40;             // sub-bucket occupancy beyond which the cell goes to the general path
 
