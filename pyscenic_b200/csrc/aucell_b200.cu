@@ -458,19 +458,24 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
             int ex = 0;
             std::frexp(wmax, &ex);                 // wmax = f * 2^ex, f in [0.5, 1)
             const int s1 = B - ex;                 // wmax * 2^s1 in [2^(B-1), 2^B)
-            const bool wide = std::ldexp(wmin, s1) < 8388608.0;  // smallest weight keeps < 24 bits: add a 2nd limb
-            const int s2 = s1 + B - 1;
-            acc_parts[r] = wide ? 2 : 1;
-            acc_scale.push_back(std::ldexp(1.0, -s1));
-            if (wide) acc_scale.push_back(std::ldexp(1.0, -s2));
+            // limbs: W_k = llrint(residual_{k-1} * 2^(s1 + (k-1)(B-1))).  Enough limbs that the smallest weight keeps
+            // at least 24 significant bits (relative error <= 6e-8 on every single term).
+            int parts = 1;
+            while (parts < 4 && std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < 8388608.0) ++parts;
+            if (std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < 8388608.0) {
+                aucell_plan_destroy(p);
+                return fail(AUCELL_ERR_UNSUPPORTED,
+                            "the weights of one regulon span more than ~45 orders of magnitude; cannot guarantee 1e-6");
+            }
+            acc_parts[r] = (uint8_t)parts;
+            for (int k = 0; k < parts; ++k) acc_scale.push_back(std::ldexp(1.0, -(s1 + k * (B - 1))));
             for (int64_t k = b; k < e; ++k) {
-                const double w = h_reg_weights[k];
-                const long long W1 = std::llrint(std::ldexp(w, s1));
-                if (W1 != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first, W1});
-                if (wide) {
-                    const double res = w - std::ldexp((double)W1, -s1);   // exact
-                    const long long W2 = std::llrint(std::ldexp(res, s2));
-                    if (W2 != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first + 1u, W2});
+                double res = h_reg_weights[k];
+                for (int l = 0; l < parts; ++l) {
+                    const int sl = s1 + l * (B - 1);
+                    const long long Wl = std::llrint(std::ldexp(res, sl));
+                    if (Wl != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)(first + l), Wl});
+                    res -= std::ldexp((double)Wl, -sl);    // exact: Wl * 2^-sl is res rounded to a coarser grid
                 }
             }
         }

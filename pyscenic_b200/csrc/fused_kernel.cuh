@@ -211,10 +211,10 @@ struct BucketStore {
 constexpr int kQ = kCapF / kFWarps;     // per-warp scatter queue (items): 256
 
 // Drain a warp's queue of (table entry, multiplier) items with all 32 lanes busy.
-template <bool ACC64>
+template <bool ACC64, typename QmT>
 __device__ __forceinline__ void flush_queue(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
                                             uint32_t* __restrict__ acc_hi, const uint32_t* __restrict__ qj,
-                                            const uint16_t* __restrict__ qm, int qn) {
+                                            const QmT* __restrict__ qm, int qn) {
     __syncwarp();
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < qn; i += 32) apply_entry<ACC64>(t, acc_lo, acc_hi, qj[i], (unsigned)qm[i]);
@@ -782,8 +782,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     // S8: scatter through a per-warp queue of (table entry, multiplier) items so that every lane
                     //     applies table entries (rows of the table have different lengths)
                     {
+                        // multipliers are as wide as positions: cutoff > 65535 implies 32-bit positions
                         uint32_t* const qj = h2 + warp * kQ;
-                        uint16_t* const qm = reinterpret_cast<uint16_t*>(fp) + warp * kQ;
+                        PosT* const qm = fp + warp * kQ;
                         int mine_n = 0;
 #pragma unroll
                         for (int k = 0; k < kItems; ++k) mine_n += (int)tc[k];
@@ -800,11 +801,11 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             for (int k = 0; k < kItems; ++k) {
                                 for (uint32_t i = 0; i < tc[k]; ++i) {
                                     qj[at] = tb[k] + i;
-                                    qm[at] = (uint16_t)mv[k];
+                                    qm[at] = (PosT)mv[k];
                                     ++at;
                                 }
                             }
-                            flush_queue<ACC64>(a.tab, acc_lo, acc_hi, qj, qm, total);
+                            flush_queue<ACC64, PosT>(a.tab, acc_lo, acc_hi, qj, qm, total);
                         } else {              // more table entries than the queue holds: apply them directly
 #pragma unroll
                             for (int k = 0; k < kItems; ++k)
@@ -879,6 +880,12 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             sum += (double)v1 * my_scale1;
                             acc_hi[my_first + 1] = 0u;
                             acc_lo[my_first + 1] = 0u;
+                            for (int k = 2; k < my_parts; ++k) {     // very wide weight ranges: up to 4 limbs
+                                const long long vk = (long long)(((unsigned long long)acc_hi[my_first + k] << 32) | acc_lo[my_first + k]);
+                                sum += (double)vk * __ldg(a.tab.acc_scale + my_first + k);
+                                acc_hi[my_first + k] = 0u;
+                                acc_lo[my_first + k] = 0u;
+                            }
                         }
                     } else {
                         sum = (double)acc_lo[my_first];

@@ -450,3 +450,60 @@ def test_config3_full_size_properties_and_spot_check():
     for r, c in enumerate(pick):
         X[r, ix[ip[c]:ip[c + 1]]] = dv[ip[c]:ip[c + 1]]
     assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))
+
+
+@pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.05, True), (0.97, True)])
+def test_fused_more_than_65535_genes(thr, unweighted):
+    """n_genes > 65535: 32-bit positions; thr 0.97 pushes the cutoff above 65535, where unit-weight sums no longer fit
+    32 bits (64-bit accumulators with unit weights) and zeros / negatives fall below the cutoff."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(13)
+    n_cells, n_genes = 12, 70001
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.04)
+    X[1] = 0.0
+    X[2, rs.choice(n_genes, 3000, replace=False)] = -1.0
+    X[3] = rs.randn(n_genes).astype(np.float32)
+    reg = synth.make_regulons(rs, n_genes, 25, 10, 2000, weighted=True)
+    cutoff = O.derive_rank_cutoff(thr, n_genes)
+    perm = np.random.RandomState(9).permutation(n_genes)
+    want = oracle_auc(X, perm, reg, cutoff, unweighted)
+    csr = sp.csr_matrix(X)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted) as plan:
+        got_d = plan.aucell_dense(cuda(X)).cpu().numpy()
+        got_s = plan.aucell_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.int32)),
+                                cuda(csr.data)).cpu().numpy()
+    assert np.array_equal(got_d, got_s)
+    if unweighted:
+        assert np.array_equal(got_d, want)
+    else:
+        assert_auc_close(got_d, want)
+
+
+def test_wide_weight_range_uses_second_accumulator():
+    """Weights spanning 14 orders of magnitude inside one regulon: the fixed-point scatter adds a second accumulator for
+    the residual, so cells that only hit the tiny-weight genes still meet the 1e-6 bar."""
+    rs = np.random.RandomState(3)
+    n_cells, n_genes = 32, 2000
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.1)
+    names, indptr, genes, weights = synth.make_regulons(rs, n_genes, 12, 30, 200, weighted=True)
+    weights = weights.copy()
+    for k in range(len(names)):
+        seg = slice(indptr[k], indptr[k + 1])
+        w = weights[seg]
+        w[::3] *= 1e-14                      # tiny weights next to O(1) weights
+        w[1::7] *= 1e9
+        weights[seg] = w
+    reg = (names, indptr, genes, weights)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(2).permutation(n_genes)
+    # make some cells express ONLY tiny-weight genes of regulon 0
+    tiny = genes[indptr[0]:indptr[1]][::3]
+    others = np.setdiff1d(np.arange(n_genes), genes[indptr[0]:indptr[1]])[:300]   # fill the ranks below the cutoff
+    X[0] = 0.0; X[0, tiny] = 3.0; X[0, others] = 1.0
+    X[1] = 0.0; X[1, tiny[:5]] = 1.0; X[1, others] = 2.0
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_dense(cuda(X)).cpu().numpy()
+    assert want[0, 0] > 0 and want[0, 0] < 1e-10
+    assert_auc_close(got, want)
