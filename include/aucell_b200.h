@@ -77,7 +77,9 @@ int64_t aucell_b200_max_genes(void);
  * h_reg_max_auc[n_regulons] float((rank_cutoff + 1) * weights.sum())  (ctxcore aucs); must be > 0 where valid.
  * h_reg_valid[n_regulons]  0 = fewer than 80 % of the regulon's genes are in the matrix -> column of zeros.
  * rank_cutoff              ctxcore derive_rank_cutoff: int(round(auc_threshold * n_genes)) - 1; only ranks
- *                          strictly below it contribute.  Must satisfy 0 <= rank_cutoff < n_genes.
+ *                          strictly below it contribute.  0 <= rank_cutoff <= 2^30 (AUCell itself has
+ *                          rank_cutoff < n_genes; ctxcore.recovery.aucs on a column-selected ranking matrix derives
+ *                          the cutoff from the whole genome and may exceed the number of columns).
  *                          n_regulons == 0 is allowed (ranking-only plan; rank_cutoff ignored).
  */
 int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32_t n_regulons,

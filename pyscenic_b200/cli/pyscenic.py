@@ -41,8 +41,9 @@ def aucell_command(args) -> None:
     """Calculate regulon enrichment (as AUC values) for cells."""
     _setup_logging()
     LOGGER.info("Loading expression matrix.")
-    sparse_in = bool(args.sparse) and any(s in PurePath(args.expression_mtx_fname.name).suffixes
-                                          for s in (".loom", ".h5ad"))
+    suffixes = PurePath(args.expression_mtx_fname.name).suffixes
+    # 10x MatrixMarket triplets are always consumed sparse; loom / h5ad when --sparse is given
+    sparse_in = ".mtx" in suffixes or (bool(args.sparse) and any(s in suffixes for s in (".loom", ".h5ad")))
     try:
         ex = load_exp_matrix(args.expression_mtx_fname.name, args.transpose == "yes", sparse_in,
                              args.cell_id_attribute, args.gene_attribute)

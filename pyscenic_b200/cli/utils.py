@@ -2,7 +2,8 @@
 """
 File I/O of the ``pyscenic aucell`` command (mirrors reference ``src/pyscenic/cli/utils.py``):
 
-    load_exp_matrix   utils.py:114-157   csv / tsv (always); loom / h5ad when loompy / anndata are importable
+    load_exp_matrix   utils.py:114-157   csv / tsv (always); 10x MatrixMarket triplets (additive; always sparse);
+                                         loom / h5ad when loompy / anndata are importable
     load_signatures   utils.py:205-227   gmt, dat (pickle), yaml (regulon records written by this package)
     save_matrix       utils.py:160-179   csv / tsv (loom when loompy is importable)
 
@@ -25,7 +26,7 @@ __all__ = ["load_exp_matrix", "load_signatures", "save_matrix", "suffixes_to_sep
 ATTRIBUTE_NAME_CELL_IDENTIFIER = "CellID"
 ATTRIBUTE_NAME_GENE = "Gene"
 
-_MATRIX_SUFFIXES = (".csv", ".tsv", ".loom", ".h5ad")
+_MATRIX_SUFFIXES = (".csv", ".tsv", ".loom", ".h5ad", ".mtx")
 
 
 def suffixes_to_separator(extension) -> str:
@@ -68,6 +69,40 @@ def _load_h5ad(fname, return_sparse):
     return pd.DataFrame(np.asarray(dense), index=adata.obs_names.values, columns=adata.var_names.values)
 
 
+def _first_existing(directory, names):
+    import os
+
+    for n in names:
+        p = os.path.join(directory, n)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def _load_10x_mtx(fname):
+    """10x Genomics MatrixMarket triplet: ``matrix.mtx[.gz]`` (features x barcodes) with ``features.tsv[.gz]`` /
+    ``genes.tsv`` and ``barcodes.tsv[.gz]`` next to it.  Returned as CSR cells x genes -- never densified, which is
+    what makes 10^6-cell matrices loadable at all (the reference densifies every input, cli/utils.py:82-90,140-149)."""
+    import os
+
+    import scipy.io
+    import scipy.sparse as sp
+
+    d = os.path.dirname(os.path.abspath(fname))
+    feat = _first_existing(d, ("features.tsv.gz", "features.tsv", "genes.tsv.gz", "genes.tsv"))
+    barc = _first_existing(d, ("barcodes.tsv.gz", "barcodes.tsv"))
+    if feat is None or barc is None:
+        raise ValueError('"{}": features.tsv / genes.tsv and barcodes.tsv are expected next to the .mtx file.'.format(fname))
+    ftab = pd.read_csv(feat, sep="\t", header=None)
+    genes = ftab.iloc[:, 1 if ftab.shape[1] > 1 else 0].astype(str).values
+    cells = pd.read_csv(barc, sep="\t", header=None).iloc[:, 0].astype(str).values
+    m = sp.csr_matrix(scipy.io.mmread(fname).T)
+    if m.shape != (len(cells), len(genes)):
+        raise ValueError('"{}": matrix shape {} does not match {} barcodes x {} features.'.format(
+            fname, m.shape[::-1], len(cells), len(genes)))
+    return m, genes, cells
+
+
 def load_exp_matrix(
     fname: str,
     transpose: bool = False,
@@ -87,6 +122,11 @@ def load_exp_matrix(
         return _load_loom(fname, return_sparse, attribute_name_cell_id, attribute_name_gene)
     if ".h5ad" in extension:
         return _load_h5ad(fname, return_sparse)
+    if ".mtx" in extension:
+        m, genes, cells = _load_10x_mtx(fname)
+        if return_sparse:
+            return m, genes, cells
+        return pd.DataFrame(np.asarray(m.todense()), index=cells, columns=genes)
     df = pd.read_csv(fname, sep=suffixes_to_separator(extension), header=0, index_col=0)
     return df.T if transpose else df
 

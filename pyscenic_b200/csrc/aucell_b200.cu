@@ -342,8 +342,10 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
     if (n_regulons < 0) return fail(AUCELL_ERR_INVALID, "n_regulons < 0");
     if (n_regulons > 0) {
         if (!h_reg_indptr || !h_reg_max_auc || !h_reg_valid) return fail(AUCELL_ERR_INVALID, "regulon arrays are NULL");
-        if (rank_cutoff < 0 || rank_cutoff >= n_genes)
-            return fail(AUCELL_ERR_INVALID, "rank_cutoff must satisfy 0 <= rank_cutoff < n_genes");
+        // AUCell has rank_cutoff < n_genes (ctxcore derive_rank_cutoff); ctxcore.recovery.aucs on a column-selected
+        // ranking matrix (cisTarget) derives the cutoff from the whole genome, so larger values are legal here
+        if (rank_cutoff < 0 || rank_cutoff > (int64_t)1 << 30)
+            return fail(AUCELL_ERR_INVALID, "rank_cutoff must satisfy 0 <= rank_cutoff <= 2^30");
         if (h_reg_indptr[0] != 0) return fail(AUCELL_ERR_INVALID, "reg_indptr[0] != 0");
         for (int r = 0; r < n_regulons; ++r)
             if (h_reg_indptr[r + 1] < h_reg_indptr[r]) return fail(AUCELL_ERR_INVALID, "reg_indptr not monotone");

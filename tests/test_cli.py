@@ -85,6 +85,30 @@ def test_unknown_format_exits_with_status_1(tmp_path):
     assert e.value.code == 1
 
 
+def test_10x_mtx_triplet_loads_sparse(tmp_path):
+    import gzip
+
+    import scipy.io
+    import scipy.sparse as sp
+
+    df, sigs, expr, gmt = _write_inputs(tmp_path, n_cells=25, n_genes=60)
+    d = tmp_path / "filtered_feature_bc_matrix"
+    d.mkdir()
+    scipy.io.mmwrite(str(d / "matrix.mtx"), sp.coo_matrix(df.values.T))          # features x barcodes, like 10x
+    with gzip.open(str(d / "features.tsv.gz"), "wt") as f:
+        f.write("".join("ENSG%05d\t%s\tGene Expression\n" % (j, g) for j, g in enumerate(df.columns)))
+    (d / "barcodes.tsv").write_text("".join("%s\n" % c for c in df.index))
+    m, genes, cells = load_exp_matrix(str(d / "matrix.mtx"), return_sparse=True)
+    assert sp.isspmatrix_csr(m) and m.shape == df.shape
+    assert list(genes) == list(df.columns) and list(cells) == list(df.index)
+    assert np.array_equal(np.asarray(m.todense()), df.values)
+    dense = load_exp_matrix(str(d / "matrix.mtx"))
+    assert np.array_equal(dense.values, df.values) and list(dense.columns) == list(df.columns)
+    (d / "barcodes.tsv").unlink()
+    with pytest.raises(ValueError):
+        load_exp_matrix(str(d / "matrix.mtx"))
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end_matches_oracle(tmp_path):
     df, sigs, expr, gmt = _write_inputs(tmp_path, n_cells=64, n_genes=500)
@@ -102,3 +126,17 @@ def test_cli_end_to_end_matches_oracle(tmp_path):
     got2 = pd.read_csv(out2, sep="\t", index_col=0)
     assert got2.shape == (len(sigs), df.shape[0])
     assert np.allclose(got2.T.values, want.values, rtol=1e-12, atol=0)
+    # 10x MatrixMarket input goes to the GPU as CSR
+    import scipy.io
+    import scipy.sparse as sp
+
+    d = tmp_path / "tenx"
+    d.mkdir()
+    scipy.io.mmwrite(str(d / "matrix.mtx"), sp.coo_matrix(df.values.T))
+    (d / "genes.tsv").write_text("".join("id%d\t%s\n" % (j, g) for j, g in enumerate(df.columns)))
+    (d / "barcodes.tsv").write_text("".join("%s\n" % c for c in df.index))
+    out3 = str(tmp_path / "auc_10x.csv")
+    cli.main(["aucell", str(d / "matrix.mtx"), gmt, "-o", out3, "--seed", "42", "--auc_threshold", "0.1"])
+    got3 = pd.read_csv(out3, index_col=0)
+    assert list(got3.index) == list(want.index)
+    assert np.allclose(got3.values, want.values, rtol=1e-12, atol=0)

@@ -507,3 +507,23 @@ def test_wide_weight_range_uses_second_accumulator():
         got = plan.aucell_dense(cuda(X)).cpu().numpy()
     assert want[0, 0] > 0 and want[0, 0] < 1e-10
     assert_auc_close(got, want)
+
+
+def test_recovery_aucs_matches_oracle_on_a_feature_ranking_db():
+    """ctxcore.recovery.aucs on a features x genes ranking database (the cisTarget use of the same arithmetic,
+    reference transform.py:195): ranks refer to the whole genome, the frame holds only the module's genes."""
+    from pyscenic_b200.recovery import aucs
+
+    rs = np.random.RandomState(17)
+    total_genes, n_feat, n_sel = 22284, 300, 120
+    full = np.stack([rs.permutation(total_genes) for _ in range(n_feat)]).astype(np.int32)   # motif rankings
+    sel = rs.choice(total_genes, n_sel, replace=False)
+    rnk = pd.DataFrame(full[:, sel], index=["motif%d" % i for i in range(n_feat)], columns=["g%d" % g for g in sel])
+    for w in (np.ones(n_sel), rs.lognormal(0, 1, n_sel)):
+        for thr in (0.005, 0.05):
+            got = aucs(rnk, total_genes, w, thr)
+            want = O.aucs(rnk, total_genes, w, thr)
+            if np.all(w == 1.0):
+                assert np.array_equal(got, want)
+            else:
+                assert_auc_close(got.reshape(-1, 1), want.reshape(-1, 1))
