@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -229,25 +230,40 @@ int resident_ctas(K kernel, int threads, int smem) {
     return n;
 }
 
+// Which fused kernel.  aucell_fused_kernel (512 threads, entries resident in registers) is the default: measured
+// 17.6 M cells/s on the cfg4 shape against 15.0 M cells/s for the streaming 256-thread variant
+// (aucell_fused_sel_kernel: three passes over the row + exact position pruning; fewer instructions per cell but more
+// L2 round trips, 45 % vs 57 % issue-slot utilisation).  AUCELL_B200_FUSED=streaming selects the variant for A/B runs
+// when its register capacity fits the cutoff.
+bool use_streaming_kernel(const aucell_plan* p) {
+    const char* env = getenv("AUCELL_B200_FUSED");
+    if (!env || strcmp(env, "streaming") != 0) return false;
+    const double c = (double)p->rank_cutoff;
+    return c + 8.0 * (std::sqrt(c) + 1.0) + 96.0 <= (double)kCapS;
+}
+
 template <typename ValT, typename PosT, int IN>
 int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st,
-                 int key_bytes) {
+                 int key_bytes, bool streaming) {
     int grid = 0;
-    if (p->acc64) {
-        auto k = aucell_fused_kernel<ValT, PosT, IN, true>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
-        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
-        if (rc) return rc;
-        k<<<grid, kF, smem, st>>>(a);
+    const int threads = streaming ? kS : kF;
+#define LAUNCH_FUSED(KERNEL)                                                                              \
+    do {                                                                                                  \
+        auto k = KERNEL;                                                                                  \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, threads, smem));   \
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);      \
+        if (rc) return rc;                                                                                \
+        k<<<grid, threads, smem, st>>>(a);                                                                \
+    } while (0)
+    if (streaming) {
+        if (p->acc64) LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, true>));
+        else LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, false>));
     } else {
-        auto k = aucell_fused_kernel<ValT, PosT, IN, false>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
-        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
-        if (rc) return rc;
-        k<<<grid, kF, smem, st>>>(a);
+        if (p->acc64) LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, true>));
+        else LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, false>));
     }
+#undef LAUNCH_FUSED
     g_launches.fetch_add(1);
     CK(cudaGetLastError());
     return AUCELL_OK;
@@ -270,14 +286,16 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     cudaStream_t st = (cudaStream_t)stream;
     const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
     const int pos_bytes = p->pos16 ? 2 : 4;
+    const bool streaming = use_streaming_kernel(p);
+    const int cap = streaming ? kCapS : kCapF;
 
     FusedArgs<ValT> a;
     memset(&a, 0, sizeof a);
     int off = 0;
     a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
-    a.off_h2 = off; off = align16(off + (kCapF + 1) * 4);
-    a.off_fk = off; off = align16(off + kCapF * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
-    a.off_fp = off; off = align16(off + kCapF * pos_bytes);
+    a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
+    a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
+    a.off_fp = off; off = align16(off + cap * pos_bytes);
     a.off_mixed = off; off = align16(off + kNb1 / 8);
     {
         int g = 2;
@@ -290,6 +308,7 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     const int smem = off;
     if (smem > p->smem_optin)
         return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
+
     a.dense = dense; a.row_stride = row_stride;
     a.indptr = indptr; a.indices = indices; a.data = data;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
@@ -300,8 +319,8 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
-    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
-    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes);
+    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
 }
 
 }  // namespace

@@ -224,7 +224,7 @@ def _plan_for(n_genes, perm, reg, cutoff, unweighted=False):
 
 
 @pytest.mark.parametrize("unweighted", [False, True])
-def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted):
+def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted, fused_variant):
     """Cells with fewer positive genes than the cutoff (zeros and even negatives fall below it), n_pos == cutoff,
     all-zero, NaN/inf cells; dense and CSR variants must agree bit-for-bit with each other."""
     import scipy.sparse as sp
@@ -267,8 +267,15 @@ def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted):
     assert np.array_equal(nnz_d.cpu().numpy(), np.count_nonzero(X, axis=1))
 
 
+@pytest.fixture(params=["classic", "streaming"])
+def fused_variant(request, monkeypatch):
+    """Both fused kernels: the default register-resident one and the streaming / pruning variant."""
+    monkeypatch.setenv("AUCELL_B200_FUSED", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("unweighted", [False, True])
-def test_fast_path_and_its_fallback(unweighted):
+def test_fast_path_and_its_fallback(unweighted, fused_variant):
     """The bucket-sort fast path and the cells it must hand to the general sort: many distinct near-equal values
     sharing one value bin (crowded bucket), binary data (one tie group), all-distinct data, a +inf outlier."""
     import scipy.sparse as sp
@@ -305,7 +312,7 @@ def test_fast_path_and_its_fallback(unweighted):
         assert_auc_close(got_d, want)
 
 
-def test_fused_csr_config3_shape_vs_oracle():
+def test_fused_csr_config3_shape_vs_oracle(fused_variant):
     """BASELINE.json configs[2] shape at oracle-friendly scale: 25k genes CSR ~7 % nnz, 500 regulons incl.
     repressor (-) regulons, weighted; per-cell nnz log-normal so some cells sit below the cutoff of 1,249."""
     n_cells, n_genes = 256, 25000
