@@ -260,6 +260,48 @@ __device__ __forceinline__ void flush_queue(const GeneTableDev& t, uint32_t* __r
     __syncwarp();
 }
 
+// Apply the table rows (tb[k], tc[k]) with multipliers mv[k], LO <= k < HI, through the warp's queue: every lane lists
+// its rows' entries at the offsets a warp scan assigns, then all 32 lanes apply them.  When the slots hold more entries
+// than the queue (many regulons, deep cutoffs) the slot range is halved recursively.
+template <bool ACC64, typename PosT, int NI, int QCAP, int LO, int HI>
+struct ScatterRange {
+    static __device__ __forceinline__ void run(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
+                                               uint32_t* __restrict__ acc_hi, uint32_t* __restrict__ qj,
+                                               PosT* __restrict__ qm, const uint32_t (&tb)[NI], const uint32_t (&tc)[NI],
+                                               const uint32_t (&mv)[NI], int lane) {
+        int mine_n = 0;
+#pragma unroll
+        for (int k = LO; k < HI; ++k) mine_n += (int)tc[k];
+        int incl = mine_n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);     // warp-uniform
+        if (total == 0) return;
+        if (total <= QCAP) {
+            int at = incl - mine_n;
+#pragma unroll
+            for (int k = LO; k < HI; ++k) {
+                for (uint32_t i = 0; i < tc[k]; ++i) {
+                    qj[at] = tb[k] + i;
+                    qm[at] = (PosT)mv[k];
+                    ++at;
+                }
+            }
+            flush_queue<ACC64, PosT>(t, acc_lo, acc_hi, qj, qm, total);
+            return;
+        }
+        if constexpr (HI - LO > 1) {
+            ScatterRange<ACC64, PosT, NI, QCAP, LO, (LO + HI) / 2>::run(t, acc_lo, acc_hi, qj, qm, tb, tc, mv, lane);
+            ScatterRange<ACC64, PosT, NI, QCAP, (LO + HI) / 2, HI>::run(t, acc_lo, acc_hi, qj, qm, tb, tc, mv, lane);
+        } else {                          // one slot alone overflows the queue (genes in hundreds of regulons)
+            for (uint32_t i = 0; i < tc[LO]; ++i) apply_entry<ACC64>(t, acc_lo, acc_hi, tb[LO] + i, mv[LO]);
+        }
+    }
+};
+
 template <bool ACC64, int NT>
 __device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
                                                   uint32_t* __restrict__ acc_hi, double* __restrict__ out) {
@@ -818,39 +860,10 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         }
                     }
                     __syncthreads();      // h2 / fp are dead: their storage becomes the per-warp scatter queues
-                    // S8: scatter through a per-warp queue of (table entry, multiplier) items so that every lane
-                    //     applies table entries (rows of the table have different lengths)
-                    {
-                        // multipliers are as wide as positions: cutoff > 65535 implies 32-bit positions
-                        uint32_t* const qj = h2 + warp * kQ;
-                        PosT* const qm = fp + warp * kQ;
-                        int mine_n = 0;
-#pragma unroll
-                        for (int k = 0; k < kItems; ++k) mine_n += (int)tc[k];
-                        int incl = mine_n;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int tt = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += tt;
-                        }
-                        const int total = __shfl_sync(0xffffffffu, incl, 31);
-                        if (total <= kQ) {
-                            int at = incl - mine_n;
-#pragma unroll
-                            for (int k = 0; k < kItems; ++k) {
-                                for (uint32_t i = 0; i < tc[k]; ++i) {
-                                    qj[at] = tb[k] + i;
-                                    qm[at] = (PosT)mv[k];
-                                    ++at;
-                                }
-                            }
-                            flush_queue<ACC64, PosT>(a.tab, acc_lo, acc_hi, qj, qm, total);
-                        } else {              // more table entries than the queue holds: apply them directly
-#pragma unroll
-                            for (int k = 0; k < kItems; ++k)
-                                for (uint32_t i = 0; i < tc[k]; ++i) apply_entry<ACC64>(a.tab, acc_lo, acc_hi, tb[k] + i, mv[k]);
-                        }
-                    }
+                    // S8: scatter through the per-warp queue (multipliers are as wide as positions: a cutoff above
+                    //     65535 implies 32-bit positions)
+                    ScatterRange<ACC64, PosT, kItems, kQ, 0, kItems>::run(a.tab, acc_lo, acc_hi, h2 + warp * kQ,
+                                                                          fp + warp * kQ, tb, tc, mv, lane);
                 }
             }
         }

@@ -534,3 +534,19 @@ def test_recovery_aucs_matches_oracle_on_a_feature_ranking_db():
                 assert np.array_equal(got, want)
             else:
                 assert_auc_close(got.reshape(-1, 1), want.reshape(-1, 1))
+
+
+@pytest.mark.parametrize("n_regulons,thr", [(2000, 0.02), (1200, 0.2)])
+def test_regulon_count_sweep_vs_oracle(n_regulons, thr, fused_variant):
+    """BASELINE.json configs[4]: regulon-count sweep (more regulons than threads per CTA) and a deep cutoff."""
+    n_cells, n_genes = 40, 20000
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1400, seed=33, device="cuda", sigma=0.5)
+    rs = np.random.RandomState(4)
+    reg = synth.make_regulons(rs, n_genes, n_regulons, 10, 300, weighted=True)
+    cutoff = O.derive_rank_cutoff(thr, n_genes)
+    perm = np.random.RandomState(6).permutation(n_genes)
+    X = synth.csr_to_dense(indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy(), n_genes)
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+    assert_auc_close(got, want)
