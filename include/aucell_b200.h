@@ -62,7 +62,8 @@ int aucell_b200_abi_version(void);
 const char* aucell_b200_last_error(void);
 /* device_count < 0 on failure.  cc = 10*major + minor of `device`; sm_count its SM count. */
 int aucell_b200_device_info(int device, int* device_count, int* cc, int* sm_count, int64_t* smem_optin_bytes);
-/* largest n_genes the shared-memory kernels accept on this build */
+/* largest n_genes the shared-memory kernels accept on this build (~600 k); plans beyond it fail with
+ * AUCELL_ERR_UNSUPPORTED at launch */
 int64_t aucell_b200_max_genes(void);
 
 /* ---- plan: permutation + regulon tables + cutoff (host -> device, once per aucell() call) ------------

@@ -334,7 +334,12 @@ const char* aucell_b200_last_error(void) { return g_err.c_str(); }
 
 int64_t aucell_b200_launch_count(void) { return g_launches.load(); }
 
-int64_t aucell_b200_max_genes(void) { return 100000; }
+int64_t aucell_b200_max_genes(void) {
+    // per cell the kernels keep two n_genes-bit arrays (occupancy bitmap + its word prefix) in shared memory next to
+    // ~72 KB of sort state; positions are 20-bit.  With the 227 KB a CTA may use on sm_100:
+    const int64_t words = ((int64_t)227 * 1024 - (int64_t)80 * 1024) / 8;
+    return std::min<int64_t>(kMaxGenes, words * 32);
+}
 
 int aucell_b200_device_info(int device, int* device_count, int* cc, int* sm_count, int64_t* smem_optin_bytes) {
     int n = 0;

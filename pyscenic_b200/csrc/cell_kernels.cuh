@@ -22,7 +22,6 @@ constexpr int kBlock = 256;          // threads per CTA
 constexpr int kWarps = kBlock / 32;
 
 enum InputKind { IN_DENSE = 0, IN_CSR = 1 };
-enum OutputKind { OUT_RANK = 0, OUT_AUC = 1 };
 
 template <typename ValT>
 struct CellArgs {
@@ -37,7 +36,7 @@ struct CellArgs {
     int n_words;             // ceil(n_genes / 32)
     const int32_t* inv_perm; // [n_genes] gene column -> shuffled position
     // output
-    uint32_t* out_rank;      // OUT_RANK: [n_cells x n_genes], shuffled column order
+    uint32_t* out_rank;      // [n_cells x n_genes], shuffled column order
     int32_t* out_nnz;        // nullable
     // shared-memory carve-up (bytes from the dynamic smem base) and capacities
     int cap;                 // explicit-entry capacity of the smem list (power of two)

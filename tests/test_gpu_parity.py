@@ -550,3 +550,44 @@ def test_regulon_count_sweep_vs_oracle(n_regulons, thr, fused_variant):
     with _plan_for(n_genes, perm, reg, cutoff) as plan:
         got = plan.aucell_csr(indptr, indices, data).cpu().numpy()
     assert_auc_close(got, want)
+
+
+def test_c_abi_error_paths():
+    """Invalid arguments are refused with an error code + message (no silent zeros)."""
+    import ctypes
+
+    import torch
+
+    from pyscenic_b200 import _native
+    from pyscenic_b200.plan import AUCellPlan, RegulonTables
+
+    lib = _native.load()
+    n_genes = 100
+    perm = np.random.RandomState(0).permutation(n_genes)
+    bad_perm = perm.copy(); bad_perm[3] = bad_perm[4]                       # not a permutation
+    with pytest.raises(_native.AUCellNativeError, match="not a permutation"):
+        AUCellPlan(n_genes, bad_perm, None)
+    with pytest.raises(_native.AUCellNativeError):
+        AUCellPlan(n_genes, perm, None, device=999)                          # no such device
+    t = RegulonTables(names=["r"], indptr=np.array([0, 2], dtype=np.int64), cols=np.array([1, 500], dtype=np.int32),
+                      weights=None, max_auc=np.array([10.0]), valid=np.ones(1, dtype=np.uint8), rank_cutoff=5, n_genes=n_genes)
+    with pytest.raises(_native.AUCellNativeError, match="out of range"):
+        AUCellPlan(n_genes, perm, t)                                         # gene column beyond the matrix
+    t.cols = np.array([1, 2], dtype=np.int32); t.max_auc = np.array([0.0])
+    with pytest.raises(_native.AUCellNativeError, match="max_auc"):
+        AUCellPlan(n_genes, perm, t)
+    t.max_auc = np.array([10.0]); t.weights = np.array([1.0, np.inf])
+    with pytest.raises(_native.AUCellNativeError, match="finite"):
+        AUCellPlan(n_genes, perm, t)
+    # a ranking-only plan refuses AUC calls; NULL outputs are refused
+    with AUCellPlan(n_genes, perm, None) as plan:
+        x = torch.zeros((2, n_genes), dtype=torch.float32, device="cuda")
+        with pytest.raises(_native.AUCellNativeError, match="no regulons"):
+            plan.aucell_dense(x)
+        rc = lib.aucell_rank_dense_f32(plan._handle, x.data_ptr(), 2, n_genes, None, None, None)
+        assert rc == -1 and b"out_rank" in lib.aucell_b200_last_error()
+        rc = lib.aucell_rank_dense_f32(plan._handle, x.data_ptr(), 2, n_genes - 1, x.data_ptr(), None, None)
+        assert rc == -1                                                       # row_stride < n_genes
+        assert lib.aucell_rank_dense_f32(plan._handle, None, 0, n_genes, None, None, None) == 0    # empty input is fine
+    assert lib.aucell_b200_max_genes() >= 500_000
+    assert lib.aucell_b200_launch_count() > 0
