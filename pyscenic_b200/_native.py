@@ -30,8 +30,10 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler",
     "-fPIC",
-    "-shared",
 ]
+# translation units of the library (compiled in parallel, then linked into one shared object)
+TRANSLATION_UNITS = ["aucell_b200.cu", "aucell_f32_dense.cu", "aucell_f32_csr.cu", "aucell_f64_dense.cu",
+                     "aucell_f64_csr.cu"]
 
 # every symbol include/aucell_b200.h declares (tests check that the library exports each of them)
 EXPORTED_SYMBOLS = [
@@ -86,24 +88,33 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library for sm_100a in-tree.  Cross-compiles without a GPU."""
+    """Compile the CUDA library for sm_100a in-tree.  Cross-compiles without a GPU.  The translation units are
+    compiled concurrently (object files under pyscenic_b200/build/) and linked with ``nvcc -shared``."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build {} (set NVCC or add nvcc to PATH)".format(LIB_NAME))
-    cmd = (
-        [nvcc]
-        + NVCC_FLAGS
-        + ["-I", _INCLUDE, "-I", _CSRC, "-o", LIB_PATH + ".tmp", os.path.join(_CSRC, "aucell_b200.cu")]
-    )
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    obj_dir = os.path.join(_PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    procs = []
+    for tu in TRANSLATION_UNITS:
+        obj = os.path.join(obj_dir, tu.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + [
+            "-I", _INCLUDE, "-I", _CSRC, "-c", "-o", obj, os.path.join(_CSRC, tu)]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for cmd, obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n{}\n{}".format(" ".join(cmd), out))
+        if verbose:
+            print(out)
+        objs.append(obj)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH + ".tmp"] + objs
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n{}\n{}".format(" ".join(cmd), res.stdout))
-    if verbose:
-        print(res.stdout)
+        raise RuntimeError("nvcc link failed:\n{}\n{}".format(" ".join(link), res.stdout))
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 

@@ -1,338 +1,47 @@
-// aucell_b200.cu -- C-ABI of libaucell_b200.so (see include/aucell_b200.h): plan management, kernel launch
-// configuration and the host-buffer streaming pipeline.  sm_100a only; no CPU fallback.
-#include "aucell_b200.h"
-
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <atomic>
-#include <cstdio>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <mutex>
-#include <new>
-#include <string>
-#include <vector>
-
-#include "cell_kernels.cuh"
-#include "fused_kernel.cuh"
+// aucell_b200.cu -- C-ABI of libaucell_b200.so (see include/aucell_b200.h): plan management, aucell4r and the host-buffer
+// streaming pipeline.  The ranking / fused kernels are instantiated in aucell_{f32,f64}_{dense,csr}.cu.
+// sm_100a only; no CPU fallback.
+#include "launch.cuh"
 
 using namespace aucell;
+using namespace aucell_host;
 
-namespace {
-
-thread_local std::string g_err;
-std::atomic<int64_t> g_launches{0};
-
-int fail(int code, const std::string& msg) {
-    g_err = msg;
-    return code;
+namespace aucell_host {
+std::string& last_error() {
+    thread_local std::string err;
+    return err;
 }
-
-int fail_cuda(cudaError_t e, const char* what, int line) {
-    char buf[512];
-    snprintf(buf, sizeof buf, "CUDA error %d (%s) at aucell_b200.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
-    g_err = buf;
-    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? AUCELL_ERR_NO_DEVICE : AUCELL_ERR_CUDA;
-}
-
-#define CK(call)                                                          \
-    do {                                                                  \
-        cudaError_t e_ = (call);                                          \
-        if (e_ != cudaSuccess) return fail_cuda(e_, #call, __LINE__);     \
-    } while (0)
-
-constexpr int64_t kMaxGenes = 1 << 20;  // bitmap words / int positions; far above any gene annotation
-
-int next_pow2(int64_t v) {
-    int64_t p = 1;
-    while (p < v) p <<= 1;
-    return (int)p;
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-}  // namespace
-
-struct aucell_plan {
-    int device = 0;
-    int sm_count = 0;
-    int64_t smem_optin = 0;
-    int n_genes = 0;
-    int n_words = 0;
-    int64_t rank_cutoff = 0;
-    bool pos16 = true;        // shuffled positions / table entries fit uint16
-    bool weighted = false;
-    int n_regulons = 0;
-    int64_t reg_nnz = 0;
-    bool acc64 = false;       // 64-bit accumulators (weighted, or cutoff too large for exact u32 sums)
-    int n_acc = 0;
-    // device arrays
-    int32_t* d_inv_perm = nullptr;
-    uint32_t* d_tptr = nullptr;
-    unsigned long long* d_tent = nullptr;   // weighted: (W << 16) | accumulator
-    uint16_t* d_tacc16 = nullptr;           // unweighted: accumulator
-    int32_t* d_acc_first = nullptr;
-    uint8_t* d_acc_parts = nullptr;
-    double* d_acc_scale = nullptr;
-    double* d_reg_max_auc = nullptr;
-    unsigned long long* d_stats = nullptr;   // path statistics of the fused kernel (5 counters)
-    // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
-    struct HostSlot {
-        cudaStream_t st = nullptr;
-        char* buf = nullptr;       // one allocation: indptr | indices | values | auc | nnz
-        size_t bytes = 0;
-    };
-    mutable std::mutex host_mu;
-    mutable std::vector<HostSlot> host_slots;
-    // overflow scratch lists, one per stream that ever needed one
-    mutable std::mutex mu;
-    mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
-};
-
-namespace {
-
-GeneTableDev tab_of(const aucell_plan* p) {
-    GeneTableDev r;
-    r.n_regulons = p->n_regulons;
-    r.n_acc = p->n_acc;
-    r.tptr = p->d_tptr;
-    r.tent = p->d_tent;
-    r.tacc16 = p->d_tacc16;
-    r.acc_first = p->d_acc_first;
-    r.acc_parts = p->d_acc_parts;
-    r.acc_scale = p->d_acc_scale;
-    r.max_auc = p->d_reg_max_auc;
-    return r;
-}
-
-int align16(int v) { return (v + 15) & ~15; }
-
-// ---- create_rankings kernels --------------------------------------------------------------------------------
-struct RankLayout {
-    int cap = 0, off_key = 0, off_pos = 0, off_bits = 0, off_wpre = 0, total = 0, ctas_per_sm = 1;
-};
-
-int layout_rank(const aucell_plan* p, int key_bytes, int cap, RankLayout* L) {
-    const int pos_bytes = p->pos16 ? 2 : 4;
-    int off = 0;
-    L->cap = cap;
-    L->off_key = off; off = align16(off + cap * key_bytes);
-    L->off_pos = off; off = align16(off + cap * pos_bytes);
-    L->off_bits = off; off = align16(off + p->n_words * 4);
-    L->off_wpre = off; off = align16(off + p->n_words * 4);
-    L->total = off;
-    return off;
-}
-
-bool plan_rank_smem(const aucell_plan* p, int key_bytes, RankLayout* L) {
-    const int want = std::min(next_pow2(p->n_genes), 4096);
-    const int64_t sm_total = 228 * 1024;  // per SM, 1 KB reserved per resident CTA
-    for (int k = 6; k >= 1; --k) {
-        const int64_t budget = std::min<int64_t>(p->smem_optin, sm_total / k - 1024);
-        int cap = 0;
-        for (int c = 2; c <= next_pow2(p->n_genes) && c <= 32768; c <<= 1) {
-            RankLayout t;
-            if (layout_rank(p, key_bytes, c, &t) <= budget) cap = c;
-        }
-        if (cap == 0 || (cap < want && k > 1)) continue;
-        cap = std::min(cap, std::max(want, 8192));
-        layout_rank(p, key_bytes, cap, L);
-        L->ctas_per_sm = k;
-        return true;
-    }
-    return false;
-}
-
-int get_scratch(const aucell_plan* p, cudaStream_t st, int key_bytes, int grid, int scratch_cap, void** key,
-                void** pos) {
-    const int pos_bytes = p->pos16 ? 2 : 4;
-    const size_t need = (size_t)grid * scratch_cap * (key_bytes + pos_bytes);
-    std::lock_guard<std::mutex> lk(p->mu);
-    auto& slot = p->scratch[{st, key_bytes}];
-    if (slot.second < need) {
-        if (slot.first) cudaFree(slot.first);
-        slot = {nullptr, 0};
-        void* ptr = nullptr;
-        cudaError_t e = cudaMalloc(&ptr, need);
-        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)", __LINE__);
-        slot = {ptr, need};
-    }
-    *key = slot.first;
-    *pos = (char*)slot.first + (size_t)grid * scratch_cap * key_bytes;
-    return AUCELL_OK;
-}
-
-template <typename ValT, int IN>
-int run_rank(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
-             const int32_t* indices, const ValT* data, int64_t n_cells, uint32_t* out_rank, int32_t* out_nnz,
-             void* stream) {
-    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
-    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
-    if (n_cells == 0) return AUCELL_OK;
-    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
-        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
-    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
-    if (!out_rank) return fail(AUCELL_ERR_INVALID, "out_rank is NULL");
-    DeviceGuard dg(p->device);
-    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t st = (cudaStream_t)stream;
-    RankLayout L;
-    const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
-    if (!plan_rank_smem(p, key_bytes, &L))
-        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
-    const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * L.ctas_per_sm);
-    CellArgs<ValT> a;
-    memset(&a, 0, sizeof a);
-    a.dense = dense; a.row_stride = row_stride;
-    a.indptr = indptr; a.indices = indices; a.data = data;
-    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.inv_perm = p->d_inv_perm;
-    a.out_rank = out_rank; a.out_nnz = out_nnz;
-    a.cap = L.cap;
-    a.off_key = L.off_key; a.off_pos = L.off_pos; a.off_bits = L.off_bits; a.off_wpre = L.off_wpre;
-    a.scratch_cap = next_pow2(p->n_genes);
-    if (L.cap < a.scratch_cap) {
-        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);
-        if (rc) return rc;
-    }
-    if (p->pos16) {
-        auto k = aucell_rank_kernel<ValT, uint16_t, IN>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        k<<<grid, kBlock, L.total, st>>>(a);
-    } else {
-        auto k = aucell_rank_kernel<ValT, uint32_t, IN>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        k<<<grid, kBlock, L.total, st>>>(a);
-    }
-    g_launches.fetch_add(1);
-    CK(cudaGetLastError());
-    return AUCELL_OK;
-}
-
-// ---- fused AUCell kernel ------------------------------------------------------------------------------------
-// resident CTAs per SM of a kernel (registers, shared memory, threads): the persistent grid is a multiple of it
-template <typename K>
-int resident_ctas(K kernel, int threads, int smem) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+std::atomic<int64_t>& launch_counter() {
+    static std::atomic<int64_t> n{0};
     return n;
 }
-
-// Which fused kernel.  aucell_fused_kernel (512 threads, entries resident in registers) is the default: measured
-// 17.6 M cells/s on the cfg4 shape against 15.0 M cells/s for the streaming 256-thread variant
-// (aucell_fused_sel_kernel: three passes over the row + exact position pruning; fewer instructions per cell but more
-// L2 round trips, 45 % vs 57 % issue-slot utilisation).  AUCELL_B200_FUSED=streaming selects the variant for A/B runs
-// when its register capacity fits the cutoff.
-bool use_streaming_kernel(const aucell_plan* p) {
-    const char* env = getenv("AUCELL_B200_FUSED");
-    if (!env || strcmp(env, "streaming") != 0) return false;
-    const double c = (double)p->rank_cutoff;
-    return c + 8.0 * (std::sqrt(c) + 1.0) + 96.0 <= (double)kCapS;
-}
-
-template <typename ValT, typename PosT, int IN>
-int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st,
-                 int key_bytes, bool streaming) {
-    int grid = 0;
-    const int threads = streaming ? kS : kF;
-#define LAUNCH_FUSED(KERNEL)                                                                              \
-    do {                                                                                                  \
-        auto k = KERNEL;                                                                                  \
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
-        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, threads, smem));   \
-        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);      \
-        if (rc) return rc;                                                                                \
-        k<<<grid, threads, smem, st>>>(a);                                                                \
-    } while (0)
-    if (streaming) {
-        if (p->acc64) LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, true>));
-        else LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, false>));
-    } else {
-        if (p->acc64) LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, true>));
-        else LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, false>));
-    }
-#undef LAUNCH_FUSED
-    g_launches.fetch_add(1);
-    CK(cudaGetLastError());
-    return AUCELL_OK;
-}
-
-template <typename ValT, int IN>
-int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
-              const int32_t* indices, const ValT* data, int64_t n_cells, double* out_auc, int32_t* out_nnz,
-              void* stream) {
-    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
-    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
-    if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
-    if (n_cells == 0) return AUCELL_OK;
-    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
-        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
-    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
-    if (!out_auc) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
-    DeviceGuard dg(p->device);
-    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
-    const int pos_bytes = p->pos16 ? 2 : 4;
-    const bool streaming = use_streaming_kernel(p);
-    const int cap = streaming ? kCapS : kCapF;
-
-    FusedArgs<ValT> a;
-    memset(&a, 0, sizeof a);
-    int off = 0;
-    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
-    a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
-    a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
-    a.off_fp = off; off = align16(off + cap * pos_bytes);
-    a.off_mixed = off; off = align16(off + kNb1 / 8);
-    {
-        int g = 2;
-        while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
-        a.gen_cap = g;
-    }
-    a.off_bits = off; off = align16(off + p->n_words * 4);
-    a.off_wpre = off; off = align16(off + p->n_words * 4);
-    a.off_acc = off; off = align16(off + p->n_acc * 8);
-    const int smem = off;
-    if (smem > p->smem_optin)
-        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
-
-    a.dense = dense; a.row_stride = row_stride;
-    a.indptr = indptr; a.indices = indices; a.data = data;
-    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.inv_perm = p->d_inv_perm;
-    a.rank_cutoff = (int)p->rank_cutoff;
-    a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
-    a.tab = tab_of(p);
-    a.out_auc = out_auc; a.out_nnz = out_nnz;
-    a.stats = p->d_stats;
-    a.scratch_cap = next_pow2(p->n_genes);
-    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
-    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
-}
-
-}  // namespace
+// kernel launchers, one translation unit per (value type, input kind)
+#define DECL_DENSE(T, SUF)                                                                                         \
+    int rank_dense_##SUF(const aucell_plan* p, const T* d, int64_t n_cells, int64_t row_stride, uint32_t* out_rank,  \
+                         int32_t* out_nnz, void* stream);                                                          \
+    int fused_dense_##SUF(const aucell_plan* p, const T* d, int64_t n_cells, int64_t row_stride, double* out_auc,    \
+                          int32_t* out_nnz, void* stream);
+#define DECL_CSR(T, SUF)                                                                                           \
+    int rank_csr_##SUF(const aucell_plan* p, const int64_t* indptr, const int32_t* indices, const T* data,         \
+                       int64_t n_cells, uint32_t* out_rank, int32_t* out_nnz, void* stream);                       \
+    int fused_csr_##SUF(const aucell_plan* p, const int64_t* indptr, const int32_t* indices, const T* data,        \
+                        int64_t n_cells, double* out_auc, int32_t* out_nnz, void* stream);
+DECL_DENSE(float, f32)
+DECL_DENSE(double, f64)
+DECL_CSR(float, f32)
+DECL_CSR(double, f64)
+#undef DECL_DENSE
+#undef DECL_CSR
+}  // namespace aucell_host
 
 // ------------------------------------------------------------------------------------------------------
 extern "C" {
 
 int aucell_b200_abi_version(void) { return AUCELL_B200_ABI_VERSION; }
 
-const char* aucell_b200_last_error(void) { return g_err.c_str(); }
+const char* aucell_b200_last_error(void) { return last_error().c_str(); }
 
-int64_t aucell_b200_launch_count(void) { return g_launches.load(); }
+int64_t aucell_b200_launch_count(void) { return launch_counter().load(); }
 
 int64_t aucell_b200_max_genes(void) {
     // per cell the kernels keep two n_genes-bit arrays (occupancy bitmap + its word prefix) in shared memory next to
@@ -432,7 +141,7 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
         const int64_t nnz = h_reg_indptr[n_regulons];
         p->reg_nnz = nnz;
         p->acc64 = p->weighted || rank_cutoff > 65535;
-        // ---- accumulators and fixed-point weights (see cell_kernels.cuh, step 3) ------------------------
+        // ---- accumulators and fixed-point weights (see fused_kernel.cuh, SCATTER) ------------------------
         std::vector<int32_t> acc_first((size_t)n_regulons, -1);
         std::vector<uint8_t> acc_parts((size_t)n_regulons, 0);
         std::vector<double> acc_scale;
@@ -589,39 +298,39 @@ int aucell_plan_path_stats(const aucell_plan_t* p, uint64_t* out5, int reset) {
 // ---- create_rankings ---------------------------------------------------------------------------------
 int aucell_rank_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
                           uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream) {
-    return run_rank<float, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_rank, d_out_nnz, stream);
+    return rank_dense_f32(plan, d_expr, n_cells, row_stride, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
                           uint32_t* d_out_rank, int32_t* d_out_nnz, void* stream) {
-    return run_rank<double, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_rank, d_out_nnz, stream);
+    return rank_dense_f64(plan, d_expr, n_cells, row_stride, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                         const float* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
                         void* stream) {
-    return run_rank<float, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
+    return rank_csr_f32(plan, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
 }
 int aucell_rank_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                         const double* d_data, int64_t n_cells, uint32_t* d_out_rank, int32_t* d_out_nnz,
                         void* stream) {
-    return run_rank<double, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
+    return rank_csr_f64(plan, d_indptr, d_indices, d_data, n_cells, d_out_rank, d_out_nnz, stream);
 }
 
 // ---- fused aucell ------------------------------------------------------------------------------------
 int aucell_dense_f32(const aucell_plan_t* plan, const float* d_expr, int64_t n_cells, int64_t row_stride,
                      double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_fused<float, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_auc, d_out_nnz, stream);
+    return fused_dense_f32(plan, d_expr, n_cells, row_stride, d_out_auc, d_out_nnz, stream);
 }
 int aucell_dense_f64(const aucell_plan_t* plan, const double* d_expr, int64_t n_cells, int64_t row_stride,
                      double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_fused<double, IN_DENSE>(plan, d_expr, row_stride, nullptr, nullptr, nullptr, n_cells, d_out_auc, d_out_nnz, stream);
+    return fused_dense_f64(plan, d_expr, n_cells, row_stride, d_out_auc, d_out_nnz, stream);
 }
 int aucell_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                    const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_fused<float, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
+    return fused_csr_f32(plan, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
 int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                    const double* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
-    return run_fused<double, IN_CSR>(plan, nullptr, 0, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
+    return fused_csr_f64(plan, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
 
 // ---- aucell4r ----------------------------------------------------------------------------------------
@@ -649,7 +358,7 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
         const int grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));
         k<<<grid, kF, smem, st>>>(d_rank, n_cells, row_stride, p->n_genes, (int)p->rank_cutoff, reg, d_out_auc);
     }
-    g_launches.fetch_add(1);
+    launch_counter().fetch_add(1);
     CK(cudaGetLastError());
     return AUCELL_OK;
 }

@@ -1,4 +1,5 @@
-// fused_kernel.cuh -- the AUCell hot path: per-cell ranking fused with the recovery-curve AUC of every regulon.
+// fused_kernel.cuh -- the AUCell hot path: per-cell ranking fused with the recovery-curve AUC of every regulon
+// (and, in RANKS mode, create_rankings: the same ranking written out as full uint32 rows).
 //
 // Reference: pyscenic.aucell.aucell = aucell4r(create_rankings(exp_mtx, seed), ...)   src/pyscenic/aucell.py:185-213
 //            create_rankings  (pandas sample + rank(method="first", ascending=False))  src/pyscenic/aucell.py:25-51
@@ -31,7 +32,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "cell_kernels.cuh"
+#include "common.cuh"
 #include "keys.cuh"
 
 namespace aucell {
@@ -72,6 +73,7 @@ struct FusedArgs {
     uint32_t inv_ng;                    // ceil(2^32 / n_genes)
     GeneTableDev tab;
     double* out_auc;
+    uint32_t* out_rank;                 // RANKS mode (create_rankings): [n_cells x n_genes], shuffled column order
     int32_t* out_nnz;
     // dynamic shared memory carve-up
     int off_h1, off_h2, off_fk, off_fp, off_mixed, off_bits, off_wpre, off_acc;
@@ -328,7 +330,7 @@ __device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_
 }
 
 // ---- general path: all explicit entries of the cell into global scratch, bitonic sort, scatter --------------
-template <typename ValT, typename PosT, int IN, bool ACC64, int NT = kF>
+template <typename ValT, typename PosT, int IN, bool ACC64, int NT = kF, bool RANKS = false>
 __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s_bits, uint32_t* s_wpre,
                              uint32_t* acc_lo, uint32_t* acc_hi, int* s_cnt, int* s_scan, unsigned char* smem) {
     using KT = KeyOf<ValT>;
@@ -387,8 +389,9 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     }
     __syncthreads();
     const int m = s_cnt[0], n_gt = s_cnt[1];
-    const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
+    const int n_genes = a.n_genes, cutoff = RANKS ? a.n_genes : a.rank_cutoff;
     const int n_zero = n_genes - m;
+    uint32_t* const out_rank = RANKS ? a.out_rank + cell * (int64_t)n_genes : nullptr;
     int P = 2;
     while (P < m) P <<= 1;
     for (int i = m + tid; i < P; i += NT) {
@@ -414,9 +417,14 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
         }
     }
     __syncthreads();
-    const int top_pos = min(n_gt, cutoff);
-    for (int i = tid; i < top_pos; i += NT)
-        scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - i));
+    if (RANKS) {
+        // create_rankings: sorted index = rank for the positives, index + n_zero for negatives / NaN
+        for (int i = tid; i < m; i += NT) out_rank[(unsigned)lp[i]] = (uint32_t)(i < n_gt ? i : i + n_zero);
+    } else {
+        const int top_pos = min(n_gt, cutoff);
+        for (int i = tid; i < top_pos; i += NT)
+            scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - i));
+    }
     const int q_zero = cutoff - n_gt;
     if (q_zero > 0) {
         for (int w = tid; w < a.n_words; w += NT) s_bits[w] = 0u;
@@ -444,13 +452,16 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
             if (z0 >= q_zero) break;                    // words are visited in increasing order by every thread
             if (!((bw >> (p & 31)) & 1u)) {
                 const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+                if (RANKS) out_rank[p] = (uint32_t)(n_gt + z);
+                else if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
             }
         }
-        const int q_neg = q_zero - n_zero;
-        const int neg_end = q_neg > 0 ? min(m, n_gt + q_neg) : n_gt;
-        for (int i = n_gt + tid; i < neg_end; i += NT)
-            scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - (i + n_zero)));
+        if (!RANKS) {
+            const int q_neg = q_zero - n_zero;
+            const int neg_end = q_neg > 0 ? min(m, n_gt + q_neg) : n_gt;
+            for (int i = n_gt + tid; i < neg_end; i += NT)
+                scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)lp[i], (unsigned)(cutoff - (i + n_zero)));
+        }
     }
     if (a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
 }
@@ -518,7 +529,9 @@ __device__ __forceinline__ void stream_row(const RowView<ValT>& row, F f) {
 }
 
 // ---- the fused kernel ---------------------------------------------------------------------------------------
-template <typename ValT, typename PosT, int IN, bool ACC64>
+// RANKS = true turns the kernel into create_rankings: the cutoff is n_genes (every gene is ranked) and the ranks are
+// written to out_rank instead of being scattered into regulon accumulators.
+template <typename ValT, typename PosT, int IN, bool ACC64, bool RANKS = false>
 __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<ValT> a) {
     using KT = KeyOf<ValT>;
     using KeyT = typename KT::type;
@@ -545,11 +558,11 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     __shared__ int s_flag[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
+    const int n_genes = a.n_genes, cutoff = RANKS ? a.n_genes : a.rank_cutoff;
 
     for (int i = tid; i < 2 * a.tab.n_acc; i += kF) acc_lo[i] = 0u;
     // epilogue constants of "my" regulon (thread r owns regulon r when there are at most kF regulons)
-    const bool own_reg = a.tab.n_regulons <= kF;
+    const bool own_reg = !RANKS && a.tab.n_regulons <= kF;
     int my_first = -1, my_parts = 0;
     double my_scale0 = 1.0, my_scale1 = 0.0, my_max_auc = 1.0;
     if (own_reg && tid < a.tab.n_regulons) {
@@ -852,7 +865,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             const unsigned long long mine = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)pos[k];
                             uint32_t rank = b;
                             for (uint32_t j = b; j < e; ++j) rank += store.before(j, key[k], pos[k], mine);
-                            if ((int)rank < cutoff) {
+                            if (RANKS) {
+                                a.out_rank[cell * (int64_t)n_genes + (unsigned)pos[k]] = rank;
+                            } else if ((int)rank < cutoff) {
                                 mv[k] = (uint32_t)(cutoff - (int)rank);
                                 tb[k] = __ldg(a.tab.tptr + (unsigned)pos[k]);
                                 tc[k] = __ldg(a.tab.tptr + (unsigned)pos[k] + 1) - tb[k];
@@ -862,8 +877,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     __syncthreads();      // h2 / fp are dead: their storage becomes the per-warp scatter queues
                     // S8: scatter through the per-warp queue (multipliers are as wide as positions: a cutoff above
                     //     65535 implies 32-bit positions)
-                    ScatterRange<ACC64, PosT, kItems, kQ, 0, kItems>::run(a.tab, acc_lo, acc_hi, h2 + warp * kQ,
-                                                                          fp + warp * kQ, tb, tc, mv, lane);
+                    if (!RANKS)
+                        ScatterRange<ACC64, PosT, kItems, kQ, 0, kItems>::run(a.tab, acc_lo, acc_hi, h2 + warp * kQ,
+                                                                              fp + warp * kQ, tb, tc, mv, lane);
                 }
             }
         }
@@ -904,7 +920,8 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 if (z0 >= q_zero) break;
                 if (!((bw >> (p & 31)) & 1u)) {
                     const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                    if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+                    if (RANKS) a.out_rank[cell * (int64_t)n_genes + p] = (uint32_t)(n_gt + z);     // coalesced
+                    else if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
                 }
             }
         }
@@ -915,9 +932,10 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         }
         if (general) {
             __syncthreads();
-            general_cell<ValT, PosT, IN, ACC64>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan, smem);
+            general_cell<ValT, PosT, IN, ACC64, kF, RANKS>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan, smem);
         }
         __syncthreads();
+        if (RANKS) continue;              // nothing to reduce: the ranks are already in global memory
         if (own_reg) {
             if (tid < a.tab.n_regulons) {
                 double res = 0.0;
@@ -955,6 +973,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     }
 }
 
+#ifdef AUCELL_B200_WITH_STREAMING
 // ---- the fused kernel, streaming variant --------------------------------------------------------------------
 // Same algorithm, organised so that registers only ever hold the entries that can rank below the cutoff:
 //   * 256 threads per CTA (4 CTAs resident per SM: four independent cells overlap each other's barriers and latencies);
@@ -965,7 +984,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 //     S* = q + 8*sqrt(q) + 32 position sub-buckets are kept, q = cutoff - (entries in earlier bins).  Sub-buckets are
 //     equal slices of the shuffled position range, so the first S* of them contain ~S* entries; the kernel verifies
 //     that they contain at least q (else the cell takes the general path), which makes the pruning exact.
-// Used when rank_cutoff + 8*sqrt(rank_cutoff) + 96 <= kCapS; larger cutoffs use aucell_fused_kernel.
+// Measured SLOWER than aucell_fused_kernel in round 1 (15.0 vs 17.6 M cells/s; fewer instructions but 45 % issue-slot
+// utilisation), so it is not part of the default build: compile with -DAUCELL_B200_WITH_STREAMING and run with
+// AUCELL_B200_FUSED=streaming to A/B it (usable when rank_cutoff + 8*sqrt(rank_cutoff) + 96 <= kCapS).
 constexpr int kS = 256;
 constexpr int kSWarps = kS / 32;
 constexpr int kSItems = 8;
@@ -1307,6 +1328,8 @@ __global__ void __launch_bounds__(kS, 4) aucell_fused_sel_kernel(const FusedArgs
         __syncthreads();
     }
 }
+
+#endif  // AUCELL_B200_WITH_STREAMING
 
 // aucell4r path: AUCs from an existing ranking matrix (reference aucell.py:98-182; ctxcore auc2d): the same
 // scatter, driven straight from the ranking row (T is indexed by the ranking matrix' own columns).

@@ -1,0 +1,333 @@
+// launch.cuh -- plan object, error helpers and the kernel launchers shared by the translation units of
+// libaucell_b200.so (aucell_b200.cu: C-ABI + float32 kernels; aucell_f64.cu: float64 kernels).  Splitting the
+// instantiations lets the two halves compile in parallel.
+#pragma once
+#include "aucell_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fused_kernel.cuh"
+
+namespace aucell_host {
+
+using namespace aucell;
+
+// defined once, in aucell_b200.cu
+std::string& last_error();                 // thread-local message of the last failure
+std::atomic<int64_t>& launch_counter();
+
+inline int fail(int code, const std::string& msg) {
+    last_error() = msg;
+    return code;
+}
+
+inline int fail_cuda(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at libaucell_b200 line %d: %s", (int)e, cudaGetErrorString(e), line, what);
+    last_error() = buf;
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? AUCELL_ERR_NO_DEVICE : AUCELL_ERR_CUDA;
+}
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call, __LINE__);     \
+    } while (0)
+
+constexpr int64_t kMaxGenes = 1 << 20;  // bitmap words / int positions; far above any gene annotation
+
+inline int next_pow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return (int)p;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace aucell_host
+
+struct aucell_plan {
+    int device = 0;
+    int sm_count = 0;
+    int64_t smem_optin = 0;
+    int n_genes = 0;
+    int n_words = 0;
+    int64_t rank_cutoff = 0;
+    bool pos16 = true;        // shuffled positions / table entries fit uint16
+    bool weighted = false;
+    int n_regulons = 0;
+    int64_t reg_nnz = 0;
+    bool acc64 = false;       // 64-bit accumulators (weighted, or cutoff too large for exact u32 sums)
+    int n_acc = 0;
+    // device arrays
+    int32_t* d_inv_perm = nullptr;
+    uint32_t* d_tptr = nullptr;
+    unsigned long long* d_tent = nullptr;   // weighted: (W << 16) | accumulator
+    uint16_t* d_tacc16 = nullptr;           // unweighted: accumulator
+    int32_t* d_acc_first = nullptr;
+    uint8_t* d_acc_parts = nullptr;
+    double* d_acc_scale = nullptr;
+    double* d_reg_max_auc = nullptr;
+    unsigned long long* d_stats = nullptr;   // path statistics of the fused kernel (5 counters)
+    // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
+    struct HostSlot {
+        cudaStream_t st = nullptr;
+        char* buf = nullptr;       // one allocation: indptr | indices | values | auc | nnz
+        size_t bytes = 0;
+    };
+    mutable std::mutex host_mu;
+    mutable std::vector<HostSlot> host_slots;
+    // overflow scratch lists, one per stream that ever needed one
+    mutable std::mutex mu;
+    mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
+};
+
+namespace aucell_host {
+
+inline GeneTableDev tab_of(const aucell_plan* p) {
+    GeneTableDev r;
+    r.n_regulons = p->n_regulons;
+    r.n_acc = p->n_acc;
+    r.tptr = p->d_tptr;
+    r.tent = p->d_tent;
+    r.tacc16 = p->d_tacc16;
+    r.acc_first = p->d_acc_first;
+    r.acc_parts = p->d_acc_parts;
+    r.acc_scale = p->d_acc_scale;
+    r.max_auc = p->d_reg_max_auc;
+    return r;
+}
+
+inline int align16(int v) { return (v + 15) & ~15; }
+
+inline int get_scratch(const aucell_plan* p, cudaStream_t st, int key_bytes, int grid, int scratch_cap, void** key,
+                void** pos) {
+    const int pos_bytes = p->pos16 ? 2 : 4;
+    const size_t need = (size_t)grid * scratch_cap * (key_bytes + pos_bytes);
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto& slot = p->scratch[{st, key_bytes}];
+    if (slot.second < need) {
+        if (slot.first) cudaFree(slot.first);
+        slot = {nullptr, 0};
+        void* ptr = nullptr;
+        cudaError_t e = cudaMalloc(&ptr, need);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)", __LINE__);
+        slot = {ptr, need};
+    }
+    *key = slot.first;
+    *pos = (char*)slot.first + (size_t)grid * scratch_cap * key_bytes;
+    return AUCELL_OK;
+}
+
+// ---- fused AUCell kernel ------------------------------------------------------------------------------------
+// resident CTAs per SM of a kernel (registers, shared memory, threads): the persistent grid is a multiple of it
+template <typename K>
+int resident_ctas(K kernel, int threads, int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+// Which fused kernel.  aucell_fused_kernel (512 threads, entries resident in registers) is the default: measured
+// 17.6 M cells/s on the cfg4 shape against 15.0 M cells/s for the streaming 256-thread variant
+// (aucell_fused_sel_kernel: three passes over the row + exact position pruning; fewer instructions per cell but more
+// L2 round trips, 45 % vs 57 % issue-slot utilisation).  AUCELL_B200_FUSED=streaming selects the variant for A/B runs
+// when its register capacity fits the cutoff.
+inline bool use_streaming_kernel(const aucell_plan* p) {
+#ifndef AUCELL_B200_WITH_STREAMING
+    (void)p;
+    return false;
+#else
+    const char* env = getenv("AUCELL_B200_FUSED");
+    if (!env || strcmp(env, "streaming") != 0) return false;
+    const double c = (double)p->rank_cutoff;
+    return c + 8.0 * (std::sqrt(c) + 1.0) + 96.0 <= (double)kCapS;
+#endif
+}
+
+template <typename ValT, typename PosT, int IN>
+int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st,
+                 int key_bytes, bool streaming) {
+    int grid = 0;
+#ifdef AUCELL_B200_WITH_STREAMING
+    const int threads = streaming ? kS : kF;
+    const int cap_unused = 0; (void)cap_unused;
+#else
+    const int threads = kF;
+#endif
+#define LAUNCH_FUSED(KERNEL)                                                                              \
+    do {                                                                                                  \
+        auto k = KERNEL;                                                                                  \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, threads, smem));   \
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);      \
+        if (rc) return rc;                                                                                \
+        k<<<grid, threads, smem, st>>>(a);                                                                \
+    } while (0)
+#ifdef AUCELL_B200_WITH_STREAMING
+    if (streaming) {
+        if (p->acc64) LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, true>));
+        else LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, false>));
+    } else
+#endif
+    {
+        if (p->acc64) LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, true>));
+        else LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, false>));
+    }
+#undef LAUNCH_FUSED
+    launch_counter().fetch_add(1);
+    CK(cudaGetLastError());
+    return AUCELL_OK;
+}
+
+template <typename ValT, int IN>
+int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
+              const int32_t* indices, const ValT* data, int64_t n_cells, double* out_auc, int32_t* out_nnz,
+              void* stream) {
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
+    if (n_cells == 0) return AUCELL_OK;
+    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
+        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
+    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (!out_auc) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
+    const int pos_bytes = p->pos16 ? 2 : 4;
+    const bool streaming = use_streaming_kernel(p);
+#ifdef AUCELL_B200_WITH_STREAMING
+    const int cap = streaming ? kCapS : kCapF;
+#else
+    const int cap = kCapF;
+#endif
+
+    FusedArgs<ValT> a;
+    memset(&a, 0, sizeof a);
+    int off = 0;
+    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
+    a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
+    a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
+    a.off_fp = off; off = align16(off + cap * pos_bytes);
+    a.off_mixed = off; off = align16(off + kNb1 / 8);
+    {
+        int g = 2;
+        while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
+        a.gen_cap = g;
+    }
+    a.off_bits = off; off = align16(off + p->n_words * 4);
+    a.off_wpre = off; off = align16(off + p->n_words * 4);
+    a.off_acc = off; off = align16(off + p->n_acc * 8);
+    const int smem = off;
+    if (smem > p->smem_optin)
+        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
+
+    a.dense = dense; a.row_stride = row_stride;
+    a.indptr = indptr; a.indices = indices; a.data = data;
+    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
+    a.inv_perm = p->d_inv_perm;
+    a.rank_cutoff = (int)p->rank_cutoff;
+    a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
+    a.tab = tab_of(p);
+    a.out_auc = out_auc; a.out_nnz = out_nnz;
+    a.stats = p->d_stats;
+    a.scratch_cap = next_pow2(p->n_genes);
+    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+}
+
+// create_rankings through the fused kernel in RANKS mode (bucket-sort ranking of every gene).
+template <typename ValT, int IN>
+int run_rank_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
+                   const int32_t* indices, const ValT* data, int64_t n_cells, uint32_t* out_rank, int32_t* out_nnz,
+                   void* stream) {
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
+    const int pos_bytes = p->pos16 ? 2 : 4;
+    FusedArgs<ValT> a;
+    memset(&a, 0, sizeof a);
+    int off = 0;
+    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
+    a.off_h2 = off; off = align16(off + std::max((kCapF + 1) * 4, kNb1 * key_bytes));
+    a.off_fk = off; off = align16(off + kCapF * (key_bytes == 4 ? 8 : key_bytes));
+    a.off_fp = off; off = align16(off + kCapF * pos_bytes);
+    a.off_mixed = off; off = align16(off + kNb1 / 8);
+    {
+        int g = 2;
+        while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
+        a.gen_cap = g;
+    }
+    a.off_bits = off; off = align16(off + p->n_words * 4);
+    a.off_wpre = off; off = align16(off + p->n_words * 4);
+    a.off_acc = off;
+    const int smem = off;
+    if (smem > p->smem_optin)
+        return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
+    a.dense = dense; a.row_stride = row_stride;
+    a.indptr = indptr; a.indices = indices; a.data = data;
+    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
+    a.inv_perm = p->d_inv_perm;
+    a.rank_cutoff = p->n_genes;
+    a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
+    memset(&a.tab, 0, sizeof a.tab);
+    a.out_rank = out_rank; a.out_nnz = out_nnz;
+    a.stats = nullptr;
+    a.scratch_cap = next_pow2(p->n_genes);
+    int grid = 0;
+#define LAUNCH_RANK(PosT)                                                                                  \
+    do {                                                                                                   \
+        auto k = aucell_fused_kernel<ValT, PosT, IN, false, true>;                                         \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));         \
+        int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);       \
+        if (rc) return rc;                                                                                 \
+        k<<<grid, kF, smem, st>>>(a);                                                                      \
+    } while (0)
+    if (p->pos16) LAUNCH_RANK(uint16_t); else LAUNCH_RANK(uint32_t);
+#undef LAUNCH_RANK
+    launch_counter().fetch_add(1);
+    CK(cudaGetLastError());
+    return AUCELL_OK;
+}
+
+
+template <typename ValT, int IN>
+int run_rank(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
+             const int32_t* indices, const ValT* data, int64_t n_cells, uint32_t* out_rank, int32_t* out_nnz,
+             void* stream) {
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (n_cells == 0) return AUCELL_OK;
+    if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
+        return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
+    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (!out_rank) return fail(AUCELL_ERR_INVALID, "out_rank is NULL");
+    return run_rank_fused<ValT, IN>(p, dense, row_stride, indptr, indices, data, n_cells, out_rank, out_nnz, stream);
+}
+
+}  // namespace aucell_host

@@ -267,10 +267,10 @@ def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted, fused_variant):
     assert np.array_equal(nnz_d.cpu().numpy(), np.count_nonzero(X, axis=1))
 
 
-@pytest.fixture(params=["classic", "streaming"])
-def fused_variant(request, monkeypatch):
-    """Both fused kernels: the default register-resident one and the streaming / pruning variant."""
-    monkeypatch.setenv("AUCELL_B200_FUSED", request.param)
+@pytest.fixture(params=["default"])
+def fused_variant(request):
+    """Hook for A/B builds (-DAUCELL_B200_WITH_STREAMING + AUCELL_B200_FUSED=streaming); the default build has one
+    fused kernel."""
     return request.param
 
 
