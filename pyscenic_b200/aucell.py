@@ -119,17 +119,68 @@ def _run_sharded(devices: List[int], n_cells: int, work) -> None:
         raise errors[0]
 
 
-def _dense_auc_shard(plan: AUCellPlan, values: np.ndarray, out: np.ndarray, device: int) -> None:
-    if values.dtype == np.float32:
-        out[:] = plan.aucell_dense_host(values)
-        return
+def _device_chunks(values: np.ndarray, device: int, chunk_bytes: int = 256 << 20):
+    """Yield ``(c0, c1, tensor)``: consecutive cell ranges of a host matrix as CUDA tensors ``[cells x genes]`` in the
+    narrowest exact float type, without ever making a transposing copy on the host.
+
+    DataFrames usually hold their block gene-major (``to_numpy()`` is then a transposed view), and ``pd.read_csv`` gives
+    float64.  numpy would need a strided 2-byte-at-a-time copy for the transpose and three full passes for the exactness
+    check; here the host only copies contiguous row blocks in whatever order the memory already has, and the GPU does
+    the transpose, the float64 -> float32 exactness test (casting may create ties that do not exist in the input, SURVEY
+    7.3-f) and the cast."""
     import torch
 
     dev = _torch_device(device)
-    chunk = max(1, (256 << 20) // (8 * values.shape[1]))
-    for c0 in range(0, values.shape[0], chunk):
-        t = torch.from_numpy(values[c0 : c0 + chunk]).to(dev)
-        out[c0 : c0 + chunk] = plan.aucell_dense(t).cpu().numpy()
+    v = np.asarray(values)
+    if v.dtype == np.bool_ or (v.dtype.kind in "iu" and v.dtype.itemsize <= 2):
+        v = v.astype(np.float32)
+    elif v.dtype.kind in "iu":
+        if v.size and v.dtype.itemsize > 4 and np.abs(v).max() > (1 << 53):
+            raise ValueError("integer expression values beyond 2^53 are not supported")
+        v = v.astype(np.float64)
+    elif v.dtype not in (np.float32, np.float64):
+        v = v.astype(np.float64)
+    n_cells, n_genes = v.shape
+    gene_major = (not v.flags.c_contiguous) and v.T.flags.c_contiguous
+    chunk = max(1, chunk_bytes // (v.dtype.itemsize * max(n_genes, 1)))
+
+    def finish(t):
+        if t.dtype == torch.float64:
+            t32 = t.to(torch.float32)
+            if bool(((t32.to(torch.float64) == t) | torch.isnan(t)).all().item()):
+                return t32     # every value of these cells survives the cast: same ranking, half the bytes
+        return t
+
+    if gene_major:
+        vt = v.T                                      # [genes x cells], C-contiguous: the memory as it is
+        free_bytes, _ = torch.cuda.mem_get_info(dev)
+        if vt.nbytes <= free_bytes // 4:
+            # upload the block as it lies in memory (contiguous gene rows, no host copy), transpose slices on the GPU
+            tdtype = torch.float32 if v.dtype == np.float32 else torch.float64
+            full = torch.empty((n_genes, n_cells), dtype=tdtype, device=dev)
+            rows = max(1, chunk_bytes // (v.dtype.itemsize * max(n_cells, 1)))
+            for g0 in range(0, n_genes, rows):
+                full[g0 : g0 + rows].copy_(torch.from_numpy(vt[g0 : g0 + rows]), non_blocking=True)
+            for c0 in range(0, n_cells, chunk):
+                c1 = min(n_cells, c0 + chunk)
+                yield c0, c1, finish(full[:, c0:c1].t().contiguous())
+            return
+        for c0 in range(0, n_cells, chunk):
+            c1 = min(n_cells, c0 + chunk)
+            # rows of the gene-major block are contiguous runs of cells: a plain block copy, then transpose on the GPU
+            yield c0, c1, finish(torch.from_numpy(np.ascontiguousarray(vt[:, c0:c1])).to(dev).t().contiguous())
+        return
+    for c0 in range(0, n_cells, chunk):
+        c1 = min(n_cells, c0 + chunk)
+        yield c0, c1, finish(torch.from_numpy(np.ascontiguousarray(v[c0:c1])).to(dev))
+
+
+def _dense_auc_shard(plan: AUCellPlan, values: np.ndarray, out: np.ndarray, device: int) -> None:
+    if values.dtype == np.float32 and values.flags.c_contiguous:
+        out[:] = plan.aucell_dense_host(values)       # library streams the host buffer itself
+        return
+    for c0, c1, t in _device_chunks(values, device):
+        out[c0:c1] = plan.aucell_dense(t).cpu().numpy()
 
 
 def _csr_auc_shard(plan: AUCellPlan, indptr, indices, data, out: np.ndarray, device: int) -> None:
@@ -193,17 +244,10 @@ def create_rankings(ex_mtx: pd.DataFrame, seed=None, *, device: int = 0) -> pd.D
     """
     n_cells, n_genes = ex_mtx.shape
     perm = permutation_from_seed(n_genes, seed)
-    values = _dense_values(ex_mtx.to_numpy())
     out = np.empty((n_cells, n_genes), dtype=np.uint32)
-    import torch
-
-    dev = _torch_device(device)
     with AUCellPlan(n_genes, perm, None, device=device) as plan:
-        chunk = max(1, (256 << 20) // (values.dtype.itemsize * max(n_genes, 1)))
-        for c0 in range(0, n_cells, chunk):
-            t = torch.from_numpy(values[c0 : c0 + chunk]).to(dev)
-            r = plan.rank_dense(t)
-            out[c0 : c0 + chunk] = r.cpu().numpy().view(np.uint32)
+        for c0, c1, t in _device_chunks(ex_mtx.to_numpy(), device):
+            out[c0:c1] = plan.rank_dense(t).cpu().numpy().view(np.uint32)
     return pd.DataFrame(data=out, index=ex_mtx.index, columns=ex_mtx.columns[perm])
 
 
@@ -343,7 +387,7 @@ def aucell(
                     _csr_auc_shard(plan, indptr[c0 : c1 + 1], indices, data, out[c0:c1], device)
 
         else:
-            values = _dense_values(exp_mtx.to_numpy())
+            values = exp_mtx.to_numpy()               # a view; dtype / layout are dealt with chunk by chunk on the GPU
 
             def work(device, c0, c1):
                 with AUCellPlan(n_genes, perm, tables, device=device) as plan:
