@@ -119,6 +119,17 @@ def _run_sharded(devices: List[int], n_cells: int, work) -> None:
         raise errors[0]
 
 
+def _from_numpy(a: np.ndarray):
+    """torch view of a host array that is only ever read (pandas hands out read-only arrays under copy-on-write)."""
+    import warnings
+
+    import torch
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(a)
+
+
 def _device_chunks(values: np.ndarray, device: int, chunk_bytes: int = 256 << 20):
     """Yield ``(c0, c1, tensor)``: consecutive cell ranges of a host matrix as CUDA tensors ``[cells x genes]`` in the
     narrowest exact float type, without ever making a transposing copy on the host.
@@ -160,7 +171,7 @@ def _device_chunks(values: np.ndarray, device: int, chunk_bytes: int = 256 << 20
             full = torch.empty((n_genes, n_cells), dtype=tdtype, device=dev)
             rows = max(1, chunk_bytes // (v.dtype.itemsize * max(n_cells, 1)))
             for g0 in range(0, n_genes, rows):
-                full[g0 : g0 + rows].copy_(torch.from_numpy(vt[g0 : g0 + rows]), non_blocking=True)
+                full[g0 : g0 + rows].copy_(_from_numpy(vt[g0 : g0 + rows]), non_blocking=True)
             for c0 in range(0, n_cells, chunk):
                 c1 = min(n_cells, c0 + chunk)
                 yield c0, c1, finish(full[:, c0:c1].t().contiguous())
@@ -168,11 +179,11 @@ def _device_chunks(values: np.ndarray, device: int, chunk_bytes: int = 256 << 20
         for c0 in range(0, n_cells, chunk):
             c1 = min(n_cells, c0 + chunk)
             # rows of the gene-major block are contiguous runs of cells: a plain block copy, then transpose on the GPU
-            yield c0, c1, finish(torch.from_numpy(np.ascontiguousarray(vt[:, c0:c1])).to(dev).t().contiguous())
+            yield c0, c1, finish(_from_numpy(np.ascontiguousarray(vt[:, c0:c1])).to(dev).t().contiguous())
         return
     for c0 in range(0, n_cells, chunk):
         c1 = min(n_cells, c0 + chunk)
-        yield c0, c1, finish(torch.from_numpy(np.ascontiguousarray(v[c0:c1])).to(dev))
+        yield c0, c1, finish(_from_numpy(np.ascontiguousarray(v[c0:c1])).to(dev))
 
 
 def _dense_auc_shard(plan: AUCellPlan, values: np.ndarray, out: np.ndarray, device: int) -> None:
