@@ -234,11 +234,11 @@ class AUCellPlan:
         return (out, nnz) if want_nnz else out
 
     # ------------------------------------------------------------------ device buffers (torch CUDA tensors)
-    @staticmethod
-    def _stream_ptr(stream):
+    def _stream_ptr(self, stream):
         import torch
 
-        s = torch.cuda.current_stream() if stream is None else stream
+        # the current stream OF THE PLAN'S DEVICE (a worker thread of a multi-GPU call has device 0 current)
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
         return ctypes.c_void_p(s.cuda_stream)
 
     def _dense_fn(self, t, prefix):
