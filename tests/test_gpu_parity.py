@@ -591,3 +591,15 @@ def test_c_abi_error_paths():
         assert lib.aucell_rank_dense_f32(plan._handle, None, 0, n_genes, None, None, None) == 0    # empty input is fine
     assert lib.aucell_b200_max_genes() >= 500_000
     assert lib.aucell_b200_launch_count() > 0
+
+
+def test_randomised_differential_fuzz_short():
+    """A short run of scripts/fuzz_gpu.py (random shapes, densities, value distributions, thresholds, regulon sets; every
+    entry point against the oracle).  The round-1 long run covered 9,253 cases (profiles/r1_fuzz_gpu.txt)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_gpu.py"), "12", "7"], cwd=root,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:]
