@@ -466,6 +466,27 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     if (a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
 }
 
+// Run f(SlotIdx<k>) for k = nk-1 ... 0 with ONE multi-way branch (Duff's device) instead of a `k < nk` test per slot:
+// item slots >= nk hold nothing, and nk is uniform over the CTA.
+template <int K>
+struct SlotIdx { static constexpr int value = K; };
+
+template <int NI, typename F>
+__device__ __forceinline__ void for_slots(int nk, F&& f) {
+    static_assert(NI == 8, "for_slots is written out for 8 item slots");
+    switch (nk) {
+        default: f(SlotIdx<7>{}); [[fallthrough]];
+        case 7: f(SlotIdx<6>{}); [[fallthrough]];
+        case 6: f(SlotIdx<5>{}); [[fallthrough]];
+        case 5: f(SlotIdx<4>{}); [[fallthrough]];
+        case 4: f(SlotIdx<3>{}); [[fallthrough]];
+        case 3: f(SlotIdx<2>{}); [[fallthrough]];
+        case 2: f(SlotIdx<1>{}); [[fallthrough]];
+        case 1: f(SlotIdx<0>{}); [[fallthrough]];
+        case 0: break;
+    }
+}
+
 // ---- row access ---------------------------------------------------------------------------------------------
 template <typename ValT>
 struct RowView {
@@ -608,21 +629,17 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 ValT v[kItems];
                 int c[kItems];
 #pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    v[k] = (ValT)0; c[k] = 0;
-                    if (k < nk) {
-                        const int i = k * kF + tid;
-                        if (i < row.count) { v[k] = row.vals[i]; c[k] = row.cols[i]; }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    key[k] = KT::KEY_ZERO; pos[k] = (PosT)0;
-                    if (k < nk) {
-                        key[k] = KT::make(v[k]);
-                        if (key[k] != KT::KEY_ZERO) pos[k] = (PosT)__ldg(a.inv_perm + c[k]);
-                    }
-                }
+                for (int k = 0; k < kItems; ++k) { v[k] = (ValT)0; c[k] = 0; key[k] = KT::KEY_ZERO; pos[k] = (PosT)0; }
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    const int i = k * kF + tid;
+                    if (i < row.count) { v[k] = row.vals[i]; c[k] = row.cols[i]; }
+                });
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    key[k] = KT::make(v[k]);
+                    if (key[k] != KT::KEY_ZERO) pos[k] = (PosT)__ldg(a.inv_perm + c[k]);
+                });
             }
         } else {
             // dense row: compact the non-zero values into the staging arrays while taking the statistics
@@ -662,16 +679,15 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------------
         if (direct) {
             if (IN == IN_CSR) {
-#pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    if (k >= nk) continue;
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
                     c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
                     if (key[k] < KT::KEY_ZERO) {
                         ++c_pos;
                         kmin = tmin(kmin, key[k]);
                         kmax = tmax(kmax, key[k]);
                     }
-                }
+                });
             }
         } else if (IN == IN_CSR) {
             stream_row(row, [&](bool ex, KeyT kk, int) {
@@ -712,14 +728,14 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             const int shift = max(0, nbits - kNb1Log);
             // S1: level-1 histogram, one representative key per bin
             if (direct) {
-#pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    if (k < nk && key[k] < KT::KEY_ZERO) {
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    if (key[k] < KT::KEY_ZERO) {
                         const uint32_t b = (uint32_t)((key[k] - kmin) >> shift);
                         atomicAdd(&h1[b], 1u);
                         rep[b] = key[k];
                     }
-                }
+                });
             } else {
                 stream_row(row, [&](bool ex, KeyT kk, int) {
                     if (ex && kk < KT::KEY_ZERO) {
@@ -733,13 +749,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             // S2: bins holding more than one distinct key (direct mode; select mode does it while selecting);
             //     exclusive scan of the bin counts; n_s = entries in the bins that start below the cutoff
             if (direct) {
-#pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    if (k < nk && key[k] < KT::KEY_ZERO) {
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    if (key[k] < KT::KEY_ZERO) {
                         const uint32_t b = (uint32_t)((key[k] - kmin) >> shift);
                         if (rep[b] != key[k]) atomicOr(&mixed[b >> 5], 1u << (b & 31));
                     }
-                }
+                });
             }
             {
                 constexpr int per = kNb1 / kF;
@@ -803,9 +819,10 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 // S4: level-2 histogram
                 uint32_t sbs[kItems];     // (sub-bucket << 8) | arrival slot ; 0xFFFFFFFF = dropped
 #pragma unroll
-                for (int k = 0; k < kItems; ++k) {
-                    sbs[k] = 0xFFFFFFFFu;
-                    if (k < nk && key[k] < KT::KEY_ZERO) {
+                for (int k = 0; k < kItems; ++k) sbs[k] = 0xFFFFFFFFu;
+                for_slots<kItems>(nk, [&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    if (key[k] < KT::KEY_ZERO) {
                         const uint32_t bin = (uint32_t)((key[k] - kmin) >> shift);
                         const uint32_t base = h1[bin];
                         if ((int)base < cutoff) {
@@ -821,7 +838,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             sbs[k] = (sb << 8) | min(got, 255u);
                         }
                     }
-                }
+                });
                 __syncthreads();
                 if (s_flag[0]) {
                     general = true;       // crowded sub-bucket (uniform decision: read after the barrier)
@@ -844,22 +861,23 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     }
                     __syncthreads();
                     // S6: entries into sub-bucket order (sub-buckets starting at or beyond the cutoff are dropped)
-#pragma unroll
-                    for (int k = 0; k < kItems; ++k) {
-                        if (k < nk && sbs[k] != 0xFFFFFFFFu) {
+                    for_slots<kItems>(nk, [&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        if (sbs[k] != 0xFFFFFFFFu) {
                             const uint32_t b2 = h2[sbs[k] >> 8];
                             if ((int)b2 < cutoff) store.put(b2 + (sbs[k] & 255u), key[k], pos[k]);
                             else sbs[k] = 0xFFFFFFFFu;
                         }
-                    }
+                    });
                     __syncthreads();
                     // S7: exact rank inside the sub-bucket -> multiplier cutoff - rank (0 = not below the cutoff),
                     //     and the gene's row of the regulon table
                     uint32_t mv[kItems], tb[kItems], tc[kItems];
 #pragma unroll
-                    for (int k = 0; k < kItems; ++k) {
-                        mv[k] = 0u; tb[k] = 0u; tc[k] = 0u;
-                        if (k < nk && sbs[k] != 0xFFFFFFFFu) {
+                    for (int k = 0; k < kItems; ++k) { mv[k] = 0u; tb[k] = 0u; tc[k] = 0u; }
+                    for_slots<kItems>(nk, [&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        if (sbs[k] != 0xFFFFFFFFu) {
                             const uint32_t sb = sbs[k] >> 8;
                             const uint32_t b = h2[sb], e = h2[sb + 1];
                             const unsigned long long mine = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)pos[k];
@@ -873,7 +891,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                                 tc[k] = __ldg(a.tab.tptr + (unsigned)pos[k] + 1) - tb[k];
                             }
                         }
-                    }
+                    });
                     __syncthreads();      // h2 / fp are dead: their storage becomes the per-warp scatter queues
                     // S8: scatter through the per-warp queue (multipliers are as wide as positions: a cutoff above
                     //     65535 implies 32-bit positions)
