@@ -136,6 +136,12 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
     PCK(cudaMemset(p->d_stats, 0, 8 * sizeof(unsigned long long)));
     PCK(cudaMalloc(&p->d_inv_perm, sizeof(int32_t) * n_genes));
     PCK(cudaMemcpy(p->d_inv_perm, inv.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice));
+    if (p->pos16) {
+        std::vector<uint16_t> inv16((size_t)n_genes);
+        for (int64_t g = 0; g < n_genes; ++g) inv16[g] = (uint16_t)inv[g];
+        PCK(cudaMalloc(&p->d_inv_perm16, sizeof(uint16_t) * n_genes));
+        PCK(cudaMemcpy(p->d_inv_perm16, inv16.data(), sizeof(uint16_t) * n_genes, cudaMemcpyHostToDevice));
+    }
 
     if (n_regulons > 0) {
         const int64_t nnz = h_reg_indptr[n_regulons];
@@ -269,6 +275,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     DeviceGuard dg(p->device);
     cudaFree(p->d_stats);
     cudaFree(p->d_inv_perm);
+    cudaFree(p->d_inv_perm16);
     cudaFree(p->d_tptr);
     cudaFree(p->d_tent);
     cudaFree(p->d_tacc16);

@@ -68,7 +68,8 @@ struct FusedArgs {
     int64_t n_cells;
     int n_genes;
     int n_words;
-    const int32_t* inv_perm;
+    const void* inv_perm;               // [n_genes] shuffled position of a column, as PosT (uint16 when it fits:
+                                        // half the footprint of the gather table in L1)
     int rank_cutoff;
     uint32_t inv_ng;                    // ceil(2^32 / n_genes)
     GeneTableDev tab;
@@ -253,7 +254,7 @@ __device__ __forceinline__ void flush_queue(const GeneTableDev& t, uint32_t* __r
                 uint32_t hi = (uint32_t)(c >> 32);
                 const uint32_t old = atomicAdd(&acc_lo[r], lo);
                 hi += (old + lo < old) ? 1u : 0u;
-                if (hi) atomicAdd(&acc_hi[r], hi);
+                atomicAdd(&acc_hi[r], hi);        // unconditional: hi is rarely 0, and a branch costs more than the add
             } else {
                 atomicAdd(&acc_lo[(uint32_t)ent[u]], mval[u]);
             }
@@ -383,7 +384,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
                 const int idx = wbase + __popc(mk & lanemask_lt());
                 const int g = (IN == IN_DENSE) ? (int)i : cols[i];
                 lk[idx] = key;
-                lp[idx] = (PosT)a.inv_perm[g];
+                lp[idx] = static_cast<const PosT*>(a.inv_perm)[g];
             }
         }
     }
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 for_slots<kItems>(nk, [&](auto K) {
                     constexpr int k = decltype(K)::value;
                     key[k] = KT::make(v[k]);
-                    if (key[k] != KT::KEY_ZERO) pos[k] = (PosT)__ldg(a.inv_perm + c[k]);
+                    pos[k] = __ldg(static_cast<const PosT*>(a.inv_perm) + c[k]);      // unconditional: padding slots read inv_perm[0]
                 });
             }
         } else {
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     const int idx = wbase + __popc(mk & lanemask_lt());
                     if (ex && idx < kCapF) {
                         fk[idx] = kk;
-                        fp[idx] = (PosT)__ldg(a.inv_perm + col);
+                        fp[idx] = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
                     }
                 }
             });
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             if (keep) {
                                 const int idx = wbase + __popc(mk & lanemask_lt());
                                 fk[idx] = kk;
-                                fp[idx] = (PosT)__ldg(a.inv_perm + col);
+                                fp[idx] = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
                             }
                         }
                     });
@@ -914,7 +915,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             } else {
                 stream_row(row, [&](bool ex, KeyT, int col) {
                     if (ex) {
-                        const unsigned p = (unsigned)__ldg(a.inv_perm + col);
+                        const unsigned p = (unsigned)__ldg(static_cast<const PosT*>(a.inv_perm) + col);
                         atomicOr(&s_bits[p >> 5], 1u << (p & 31));
                     }
                 });
@@ -1141,7 +1142,7 @@ __global__ void __launch_bounds__(kS, 4) aucell_fused_sel_kernel(const FusedArgs
                         const uint32_t b = (uint32_t)((kk - kmin) >> shift);
                         if ((int)h1[b] < cutoff) {
                             keep = true;
-                            ps = (PosT)__ldg(a.inv_perm + col);
+                            ps = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
                             const bool differs = rep[b] != kk;
                             if ((int)b == star && prune) {
                                 if (differs) s_flag[1] = 1;        // a big straddling bin must hold one key
@@ -1305,7 +1306,7 @@ __global__ void __launch_bounds__(kS, 4) aucell_fused_sel_kernel(const FusedArgs
             __syncthreads();
             stream_row<kS>(row, [&](bool ex, KeyT, int col) {
                 if (ex) {
-                    const unsigned p = (unsigned)__ldg(a.inv_perm + col);
+                    const unsigned p = (unsigned)__ldg(static_cast<const PosT*>(a.inv_perm) + col);
                     atomicOr(&s_bits[p >> 5], 1u << (p & 31));
                 }
             });

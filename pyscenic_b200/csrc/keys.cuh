@@ -34,10 +34,11 @@ struct KeyOf<float> {
 #else
         union { float f; uint32_t u; } cvt; cvt.f = v; uint32_t u = cvt.u;
 #endif
-        uint32_t mag = u & 0x7FFFFFFFu;
-        if (mag > 0x7F800000u) return KEY_NAN;
-        if (mag == 0u) return KEY_ZERO;
-        return (u >> 31) ? u : (0x7FFFFFFFu - u);
+        const uint32_t mag = u & 0x7FFFFFFFu;
+        uint32_t key = (u >> 31) ? u : (0x7FFFFFFFu - u);      // selects, no branches: this runs once per stored value
+        key = (mag == 0u) ? KEY_ZERO : key;
+        key = (mag > 0x7F800000u) ? KEY_NAN : key;
+        return key;
     }
 };
 
@@ -52,10 +53,11 @@ struct KeyOf<double> {
 #else
         union { double f; uint64_t u; } cvt; cvt.f = v; uint64_t u = cvt.u;
 #endif
-        uint64_t mag = u & 0x7FFFFFFFFFFFFFFFull;
-        if (mag > 0x7FF0000000000000ull) return KEY_NAN;
-        if (mag == 0ull) return KEY_ZERO;
-        return (u >> 63) ? u : (0x7FFFFFFFFFFFFFFFull - u);
+        const uint64_t mag = u & 0x7FFFFFFFFFFFFFFFull;
+        uint64_t key = (u >> 63) ? u : (0x7FFFFFFFFFFFFFFFull - u);
+        key = (mag == 0ull) ? KEY_ZERO : key;
+        key = (mag > 0x7FF0000000000000ull) ? KEY_NAN : key;
+        return key;
     }
 };
 

@@ -82,6 +82,7 @@ struct aucell_plan {
     int n_acc = 0;
     // device arrays
     int32_t* d_inv_perm = nullptr;
+    uint16_t* d_inv_perm16 = nullptr;       // the same as uint16 (pos16 plans)
     uint32_t* d_tptr = nullptr;
     unsigned long long* d_tent = nullptr;   // weighted: (W << 16) | accumulator
     uint16_t* d_tacc16 = nullptr;           // unweighted: accumulator
@@ -248,7 +249,7 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.dense = dense; a.row_stride = row_stride;
     a.indptr = indptr; a.indices = indices; a.data = data;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.inv_perm = p->d_inv_perm;
+    a.inv_perm = p->pos16 ? (const void*)p->d_inv_perm16 : (const void*)p->d_inv_perm;
     a.rank_cutoff = (int)p->rank_cutoff;
     a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
     a.tab = tab_of(p);
@@ -291,7 +292,7 @@ int run_rank_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, 
     a.dense = dense; a.row_stride = row_stride;
     a.indptr = indptr; a.indices = indices; a.data = data;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.inv_perm = p->d_inv_perm;
+    a.inv_perm = p->pos16 ? (const void*)p->d_inv_perm16 : (const void*)p->d_inv_perm;
     a.rank_cutoff = p->n_genes;
     a.inv_ng = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, ((1ull << 32) + (uint64_t)p->n_genes - 1) / (uint64_t)p->n_genes);
     memset(&a.tab, 0, sizeof a.tab);

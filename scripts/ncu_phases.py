@@ -13,13 +13,19 @@ for r in rows:
     try: n = int(r[hdr.index("Instructions Executed")]); s = int(r[hdr.index("# Samples")])
     except ValueError: continue
     per[(cur_file, int(r[0]))] = (n, s, r[1])
-src = open("pyscenic_b200/csrc/fused_kernel.cuh").read().splitlines()
+SRC = sys.argv[3] if len(sys.argv) > 3 else "fused_kernel.cuh"
+src = open("pyscenic_b200/csrc/" + SRC).read().splitlines()
 # phase boundaries by searching marker text
 marks = [("scan_helper", "block_excl_scan_n("), ("scatter_packed", "void scatter_packed("), ("write_aucs", "void write_aucs_packed("),
-         ("general_cell", "void general_cell("), ("kernel_prologue", "aucell_fused_kernel(const FusedArgs"), ("LOAD", "LOAD: explicit entries"),
+         ("general_cell", "void general_cell("), ("kernel_prologue", "aucell_fused_kernel(const FusedArgs"), ("LOAD", "---- LOAD ----"),
          ("stats", "cell statistics"), ("S1_hist1", "// S1:"), ("S2_mixed_scan", "// S2:"), ("S3_clear", "// S3:"), ("S4_hist2", "// S4:"),
-         ("S5_scan2", "// S5:"), ("S6_place", "// S6:"), ("S7_rank", "// S7:"), ("ZEROS", "ZEROS: fill ranks"), ("tail", "if (a.stats != nullptr && tid == 0) {"),
+         ("S5_scan2", "// S5:"), ("T1_classify", "// T1:"), ("T2_fill", "// T2:"), ("T3_scan", "// T3:"), ("T4_rank", "// T4:"), ("T4_small", "// small bins: one thread per entry"), ("S8_scatter", "// S8:"), ("emit", "auto emit = "), ("S6_place", "// S6:"), ("S7_rank", "// S7:"), ("ZEROS", "ZEROS: fill ranks"), ("tail", "if (a.stats != nullptr && tid == 0) {"),
          ("from_rankings", "aucell_from_rankings_kernel(")]
+if SRC == "plane_kernel.cuh":
+    marks = [("prologue", "aucell_plane_kernel(const PlaneArgs"), ("LOAD", "---- LOAD ----"), ("stats_reduce", "c_exp = warp_sum(c_exp);"),
+             ("S1_hist1", "// S1:"), ("S2_mixed", "// S2:"), ("S2_scan", "constexpr int per = (kNb1"), ("T1_classify", "// T1:"),
+             ("T2_fill", "// T2:"), ("T3_scan", "// T3:"), ("T4_rank", "// T4:"), ("T4_small", "if (tid < nsmall) {"),
+             ("SCATTER_expand", "// SCATTER:"), ("todo", "if (todo) {"), ("ZEROS", "---- ZEROS"), ("OUT", "---- OUT ----")]
 bounds = []
 for name, text in marks:
     for i, l in enumerate(src):
@@ -32,7 +38,7 @@ def phase(line):
     return p
 tot = sum(v[0] for v in per.values()); agg = {}
 for (f, ln), (n, s, t) in per.items():
-    k = phase(ln) if f == "fused_kernel.cuh" else f
+    k = phase(ln) if f == SRC else f
     a = agg.setdefault(k, [0, 0]); a[0] += n; a[1] += s
 tots = sum(v[1] for v in agg.values())
 print("total warp-instr %.3g (%.0f per cell)" % (tot, tot / cells))
