@@ -17,7 +17,7 @@ SRC = sys.argv[3] if len(sys.argv) > 3 else "fused_kernel.cuh"
 src = open("pyscenic_b200/csrc/" + SRC).read().splitlines()
 # phase boundaries by searching marker text
 marks = [("scan_helper", "block_excl_scan_n("), ("scatter_packed", "void scatter_packed("), ("write_aucs", "void write_aucs_packed("),
-         ("general_cell", "void general_cell("), ("kernel_prologue", "aucell_fused_kernel(const FusedArgs"), ("LOAD", "---- LOAD ----"),
+         ("general_cell", "void general_cell("), ("slot_dispatch(inlined phase bodies)", "struct SlotIdx"), ("row_stream", "struct RowView"), ("kernel_prologue", "aucell_fused_kernel(const FusedArgs"), ("LOAD", "---- LOAD ----"),
          ("stats", "cell statistics"), ("S1_hist1", "// S1:"), ("S2_mixed_scan", "// S2:"), ("S3_clear", "// S3:"), ("S4_hist2", "// S4:"),
          ("S5_scan2", "// S5:"), ("T1_classify", "// T1:"), ("T2_fill", "// T2:"), ("T3_scan", "// T3:"), ("T4_rank", "// T4:"), ("T4_small", "// small bins: one thread per entry"), ("S8_scatter", "// S8:"), ("emit", "auto emit = "), ("S6_place", "// S6:"), ("S7_rank", "// S7:"), ("ZEROS", "ZEROS: fill ranks"), ("tail", "if (a.stats != nullptr && tid == 0) {"),
          ("from_rankings", "aucell_from_rankings_kernel(")]
