@@ -229,19 +229,28 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     FusedArgs<ValT> a;
     memset(&a, 0, sizeof a);
     int off = 0;
-    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
-    a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
-    a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
-    a.off_fp = off; off = align16(off + cap * pos_bytes);
-    a.off_mixed = off; off = align16(off + kNb1 / 8);
+    if (!streaming) {
+        // aucell_fused_kernel: compile-time offsets up to the accumulators (fused_offsets), then bitmap + prefixes
+        const FusedOffsets L = fused_offsets(key_bytes, pos_bytes);
+        a.off_h1 = L.h1; a.off_h2 = L.h2; a.off_fk = L.fk; a.off_fp = L.fp; a.off_mixed = L.mixed;
+        a.off_acc = L.acc; off = align16(L.acc + p->n_acc * 8);
+        a.off_bits = off; off = align16(off + p->n_words * 4);
+        a.off_wpre = off; off = align16(off + p->n_words * 4);
+    } else {
+        a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
+        a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
+        a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
+        a.off_fp = off; off = align16(off + cap * pos_bytes);
+        a.off_mixed = off; off = align16(off + kNb1 / 8);
+        a.off_bits = off; off = align16(off + p->n_words * 4);
+        a.off_wpre = off; off = align16(off + p->n_words * 4);
+        a.off_acc = off; off = align16(off + p->n_acc * 8);
+    }
     {
         int g = 2;
         while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
         a.gen_cap = g;
     }
-    a.off_bits = off; off = align16(off + p->n_words * 4);
-    a.off_wpre = off; off = align16(off + p->n_words * 4);
-    a.off_acc = off; off = align16(off + p->n_acc * 8);
     const int smem = off;
     if (smem > p->smem_optin)
         return fail(AUCELL_ERR_UNSUPPORTED, "n_genes / n_regulons too large for the shared-memory kernels");
@@ -272,12 +281,10 @@ int run_rank_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, 
     const int pos_bytes = p->pos16 ? 2 : 4;
     FusedArgs<ValT> a;
     memset(&a, 0, sizeof a);
-    int off = 0;
-    a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
-    a.off_h2 = off; off = align16(off + std::max((kCapF + 1) * 4, kNb1 * key_bytes));
-    a.off_fk = off; off = align16(off + kCapF * (key_bytes == 4 ? 8 : key_bytes));
-    a.off_fp = off; off = align16(off + kCapF * pos_bytes);
-    a.off_mixed = off; off = align16(off + kNb1 / 8);
+    const FusedOffsets L = fused_offsets(key_bytes, pos_bytes);
+    a.off_h1 = L.h1; a.off_h2 = L.h2; a.off_fk = L.fk; a.off_fp = L.fp; a.off_mixed = L.mixed;
+    a.off_acc = L.acc;                    // no accumulators in RANKS mode
+    int off = L.acc;
     {
         int g = 2;
         while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
@@ -285,7 +292,6 @@ int run_rank_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, 
     }
     a.off_bits = off; off = align16(off + p->n_words * 4);
     a.off_wpre = off; off = align16(off + p->n_words * 4);
-    a.off_acc = off;
     const int smem = off;
     if (smem > p->smem_optin)
         return fail(AUCELL_ERR_UNSUPPORTED, "n_genes too large for the shared-memory kernels");
