@@ -130,6 +130,16 @@ int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, cons
 int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
 
+/* ---- downstream of the AUC matrix ------------------------------------------------------------------- */
+/* Regulon specificity scores (replaces pyscenic.rss.regulon_specificity_scores, reference src/pyscenic/rss.py:8-33):
+ * d_out[t * n_regulons + r] = 1 - sqrt(JSD(auc[:, r] / sum(auc[:, r]), [label == t] / count_t)), natural logarithm.
+ * d_auc: device fp64 [n_cells x row_stride] (the layout aucell_* writes); d_labels: device int32 type index per cell
+ * in [0, n_types); h_type_counts: HOST int64[n_types], cells per type (each > 0, summing to n_cells); d_out: device
+ * fp64 [n_types x n_regulons].  Asynchronous on `stream` apart from one small upload; deterministic (no atomics).
+ * A regulon whose AUCs are all zero yields NaN, as in the reference. */
+int aucell_rss_f64(int device, const double* d_auc, int64_t n_cells, int64_t row_stride, int32_t n_regulons,
+                   const int32_t* d_labels, int32_t n_types, const int64_t* h_type_counts, double* d_out, void* stream);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 /* Which code path the fused kernel took, summed over every call on this plan since the last reset (synchronises
  * the device): out5 = { cells, general path: more than 4096 explicit entries, general path: negative values ranked

@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 ]
 # translation units of the library (compiled in parallel, then linked into one shared object)
 TRANSLATION_UNITS = ["aucell_b200.cu", "aucell_f32_dense.cu", "aucell_f32_csr.cu", "aucell_f64_dense.cu",
-                     "aucell_f64_csr.cu"]
+                     "aucell_f64_csr.cu", "aucell_rss.cu"]
 
 # every symbol include/aucell_b200.h declares (tests check that the library exports each of them)
 EXPORTED_SYMBOLS = [
@@ -56,6 +56,7 @@ EXPORTED_SYMBOLS = [
     "aucell_dense_f32_host",
     "aucell_b200_launch_count",
     "aucell_plan_path_stats",
+    "aucell_rss_f64",
 ]
 
 
@@ -153,6 +154,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_plan_create.restype = c_int
         lib.aucell_plan_path_stats.argtypes = [p, p, c_int]
         lib.aucell_plan_path_stats.restype = c_int
+        lib.aucell_rss_f64.argtypes = [c_int, p, i64, i64, i32, p, i32, p, p, p]
+        lib.aucell_rss_f64.restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]
         lib.aucell_plan_destroy.restype = c_int
         for name in ("aucell_rank_dense_f32", "aucell_rank_dense_f64"):
