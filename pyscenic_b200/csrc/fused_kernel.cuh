@@ -709,13 +709,16 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             stream_dense_vec(row, [&](const KeyT (&kk)[V], int col0) {
                 // a thread's non-zeros (0..V) get consecutive staging slots: one offset computation per vector
                 // (three votes) instead of one vote + atomic per element
+                // branch-free statistics: zeros carry KEY_ZERO and negatives larger keys, so neither lowers kmin;
+                // kmax only looks at positives
                 int c = 0;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    if (kk[j] != KT::KEY_ZERO) {
-                        ++c;
-                        if (kk[j] < KT::KEY_ZERO) { ++c_pos; kmin = tmin(kmin, kk[j]); kmax = tmax(kmax, kk[j]); }
-                    }
+                    const bool ps = kk[j] < KT::KEY_ZERO;
+                    c += (kk[j] != KT::KEY_ZERO) ? 1 : 0;
+                    c_pos += ps ? 1 : 0;
+                    kmin = tmin(kmin, kk[j]);
+                    kmax = tmax(kmax, ps ? kk[j] : (KeyT)0);
                 }
                 c_exp += c;
                 const unsigned b0 = __ballot_sync(0xffffffffu, c & 1);
@@ -728,15 +731,15 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     if (lane == 0) wbase = atomicAdd(&s_cnt[0], wtot);
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
                     int idx = wbase + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                    const PosT* const ip = static_cast<const PosT*>(a.inv_perm) + col0;
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        if (kk[j] != KT::KEY_ZERO) {
-                            if (idx < kCapF) {
-                                fk[idx] = kk[j];
-                                fp[idx] = __ldg(static_cast<const PosT*>(a.inv_perm) + col0 + j);
-                            }
-                            ++idx;
+                        const bool nz = kk[j] != KT::KEY_ZERO;
+                        if (nz && idx < kCapF) {          // short body: predicated, no divergence bookkeeping
+                            fk[idx] = kk[j];
+                            fp[idx] = __ldg(ip + j);
                         }
+                        idx += nz ? 1 : 0;
                     }
                 }
             });
@@ -756,14 +759,13 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------------
         if (direct) {
             if (IN == IN_CSR) {
-                for_slots<kItems>(nk, [&](auto K) {
+                for_slots<kItems>(nk, [&](auto K) {       // branch-free: zeros / negatives never lower kmin
                     constexpr int k = decltype(K)::value;
+                    const bool ps = key[k] < KT::KEY_ZERO;
                     c_exp += (key[k] != KT::KEY_ZERO) ? 1 : 0;
-                    if (key[k] < KT::KEY_ZERO) {
-                        ++c_pos;
-                        kmin = tmin(kmin, key[k]);
-                        kmax = tmax(kmax, key[k]);
-                    }
+                    c_pos += ps ? 1 : 0;
+                    kmin = tmin(kmin, key[k]);
+                    kmax = tmax(kmax, ps ? key[k] : (KeyT)0);
                 });
             }
         } else if (IN == IN_CSR) {
