@@ -113,6 +113,10 @@ int aucell_csr_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int
                    const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
 int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
                    const double* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
+/* CSR with uint16 column indices (plans with n_genes <= 65535 only): 6 instead of 8 bytes per stored entry.  Same
+ * contract as aucell_csr_f32; it is what aucell_csr_f32_host uploads after narrowing the caller's int32 indices. */
+int aucell_csr16_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const uint16_t* d_indices,
+                     const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
 
 /* ---- aucell4r (aucell.py:98-182): AUCs from an existing uint32 ranking matrix [n_cells x n_genes]
  * (row_stride in elements).  The plan's regulon columns index the ranking matrix' columns directly (create the

@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 ]
 # translation units of the library (compiled in parallel, then linked into one shared object)
 TRANSLATION_UNITS = ["aucell_b200.cu", "aucell_f32_dense.cu", "aucell_f32_csr.cu", "aucell_f64_dense.cu",
-                     "aucell_f64_csr.cu", "aucell_rss.cu"]
+                     "aucell_f64_csr.cu", "aucell_f32_csr16.cu", "aucell_rss.cu"]
 
 # every symbol include/aucell_b200.h declares (tests check that the library exports each of them)
 EXPORTED_SYMBOLS = [
@@ -51,6 +51,7 @@ EXPORTED_SYMBOLS = [
     "aucell_dense_f64",
     "aucell_csr_f32",
     "aucell_csr_f64",
+    "aucell_csr16_f32",
     "aucell_from_rankings_u32",
     "aucell_csr_f32_host",
     "aucell_dense_f32_host",
@@ -170,7 +171,7 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
             f = getattr(lib, name)
             f.argtypes = [p, p, i64, i64, p, p, p]
             f.restype = c_int
-        for name in ("aucell_csr_f32", "aucell_csr_f64"):
+        for name in ("aucell_csr_f32", "aucell_csr_f64", "aucell_csr16_f32"):
             f = getattr(lib, name)
             f.argtypes = [p, p, p, p, i64, p, p, p]
             f.restype = c_int

@@ -3,6 +3,12 @@
 // sm_100a only; no CPU fallback.
 #include "launch.cuh"
 
+#include <chrono>
+#include <thread>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
+
 using namespace aucell;
 using namespace aucell_host;
 
@@ -32,6 +38,8 @@ DECL_CSR(float, f32)
 DECL_CSR(double, f64)
 #undef DECL_DENSE
 #undef DECL_CSR
+int fused_csr16_f32(const aucell_plan* p, const int64_t* indptr, const uint16_t* indices, const float* data,
+                    int64_t n_cells, double* out_auc, int32_t* out_nnz, void* stream);
 }  // namespace aucell_host
 
 // ------------------------------------------------------------------------------------------------------
@@ -287,6 +295,8 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     for (auto& hs : p->host_slots) {
         if (hs.st) { cudaStreamSynchronize(hs.st); cudaStreamDestroy(hs.st); }
         cudaFree(hs.buf);
+        cudaFreeHost(hs.pin_idx);
+        if (hs.idx_done) cudaEventDestroy(hs.idx_done);
     }
     delete p;
     return AUCELL_OK;
@@ -339,6 +349,11 @@ int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int
                    const double* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
     return fused_csr_f64(plan, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
+int aucell_csr16_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const uint16_t* d_indices,
+                     const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream) {
+    if (plan && !plan->pos16) return fail(AUCELL_ERR_INVALID, "uint16 column indices need n_genes <= 65535");
+    return fused_csr16_f32(plan, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
+}
 
 // ---- aucell4r ----------------------------------------------------------------------------------------
 int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int64_t n_cells, int64_t row_stride,
@@ -378,7 +393,7 @@ constexpr int kHostSlots = 4;
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Make sure the plan owns kHostSlots staging buffers of at least `bytes` each (and their streams).
-int ensure_host_slots(const aucell_plan* p, size_t bytes) {
+int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0) {
     if (p->host_slots.empty()) p->host_slots.resize(kHostSlots);
     for (auto& hs : p->host_slots) {
         if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
@@ -390,8 +405,84 @@ int ensure_host_slots(const aucell_plan* p, size_t bytes) {
             CK(cudaMalloc(&hs.buf, bytes));
             hs.bytes = bytes;
         }
+        if (hs.pin_bytes < pin_idx_bytes) {
+            CK(cudaStreamSynchronize(hs.st));
+            cudaFreeHost(hs.pin_idx);
+            hs.pin_idx = nullptr;
+            hs.pin_bytes = 0;
+            CK(cudaHostAlloc((void**)&hs.pin_idx, pin_idx_bytes, cudaHostAllocDefault));
+            hs.pin_bytes = pin_idx_bytes;
+        }
+        if (pin_idx_bytes && !hs.idx_done) CK(cudaEventCreateWithFlags(&hs.idx_done, cudaEventDisableTiming));
+        hs.idx_pending = false;
     }
     return AUCELL_OK;
+}
+
+// int32 -> uint16 column indices of one chunk, spread over host threads (the loop is memory bound: a PCIe 5 x16 link
+// wants ~27 GB/s of int32 indices narrowed).  Returns false when an index does not fit 16 bits.
+#if defined(__x86_64__) && defined(__GNUC__)
+#define AUCELL_HAVE_AVX2_PATH 1
+__attribute__((target("avx2"))) uint32_t narrow_span_avx2(const int32_t* src, uint16_t* dst, int64_t n) {
+    __m256i bad = _mm256_setzero_si256();
+    int64_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 8));
+        bad = _mm256_or_si256(bad, _mm256_or_si256(a, b));
+        // packus works inside the 128-bit halves: [a0-3 b0-3 | a4-7 b4-7] -> reorder the 64-bit quarters
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), pk);
+    }
+    alignas(32) uint32_t lanes[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(lanes), bad);
+    uint32_t any = 0;
+    for (int k = 0; k < 8; ++k) any |= lanes[k];
+    for (; i < n; ++i) {
+        const uint32_t v = (uint32_t)src[i];
+        any |= v;
+        dst[i] = (uint16_t)v;
+    }
+    return any >> 16;           // saturated lanes only occur together with a set high half, which is reported here
+}
+#endif
+
+uint32_t narrow_span(const int32_t* src, uint16_t* dst, int64_t n) {
+#ifdef AUCELL_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return narrow_span_avx2(src, dst, n);
+#endif
+    uint32_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t v = (uint32_t)src[i];
+        bad |= v >> 16;
+        dst[i] = (uint16_t)v;
+    }
+    return bad;
+}
+
+bool narrow_indices(const int32_t* src, uint16_t* dst, int64_t n, int threads) {
+    if (threads <= 1 || n < (1 << 18)) return narrow_span(src, dst, n) == 0;
+    std::vector<uint32_t> bad((size_t)threads, 0u);
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)threads - 1);
+    const int64_t per = ((n + threads - 1) / threads + 63) & ~int64_t(63);
+    for (int t = 1; t < threads; ++t) {
+        const int64_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+        pool.emplace_back([&bad, src, dst, t, b, e]() { bad[(size_t)t] = narrow_span(src + b, dst + b, e - b); });
+    }
+    bad[0] = narrow_span(src, dst, std::min(n, per));
+    for (auto& th : pool) th.join();
+    uint32_t any = 0;
+    for (uint32_t b : bad) any |= b;
+    return any == 0;
+}
+
+int host_threads() {
+    const char* env = getenv("AUCELL_B200_HOST_THREADS");
+    if (env && *env) return std::max(1, std::min(64, atoi(env)));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hw ? hw : 4u));
 }
 
 }  // namespace
@@ -427,11 +518,20 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     const size_t o_auc = align256(o_vals + sizeof(float) * std::max<int64_t>(max_nnz, 1));
     const size_t o_nnz = align256(o_auc + sizeof(double) * chunk_cells * R);
     const size_t bytes = align256(o_nnz + sizeof(int32_t) * chunk_cells);
-    int rc = ensure_host_slots(p, bytes);
+    // 16-bit positions: upload the column indices as uint16 (a quarter less PCIe traffic; the link is the bottleneck
+    // of this call).  AUCELL_B200_HOST_IDX16=0 keeps the int32 upload.
+    const char* env16 = getenv("AUCELL_B200_HOST_IDX16");
+    bool idx16 = p->pos16 && max_nnz > 0 && !(env16 && env16[0] == '0');
+    const bool idx16_forced = env16 && env16[0] == '1';
+    double narrow_ns = 0.0;               // time spent narrowing and entries narrowed so far in this call
+    int64_t narrow_n = 0;
+    int narrow_chunks = 0;
+    const int n_threads = idx16 ? host_threads() : 1;
+    int rc = ensure_host_slots(p, bytes, idx16 ? sizeof(uint16_t) * (size_t)max_nnz : 0);
     if (rc) return rc;
     int k = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
-        const aucell_plan::HostSlot& s = p->host_slots[k];
+        aucell_plan::HostSlot& s = p->host_slots[k];
         int64_t* d_indptr = reinterpret_cast<int64_t*>(s.buf + o_indptr);
         int32_t* d_indices = reinterpret_cast<int32_t*>(s.buf + o_indices);
         float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
@@ -443,12 +543,36 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
         CK(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
         if (ne > 0) {
-            CK(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+            if (idx16) {
+                if (s.idx_pending) CK(cudaEventSynchronize(s.idx_done));      // staging buffer free again
+                s.idx_pending = false;
+                const auto t0 = std::chrono::steady_clock::now();
+                if (!narrow_indices(h_indices + e0, s.pin_idx, ne, n_threads)) {
+                    rc = fail(AUCELL_ERR_INVALID, "CSR column index out of range");
+                    break;
+                }
+                narrow_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+                narrow_n += ne;
+                ++narrow_chunks;
+                CK(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, s.st));
+                CK(cudaEventRecord(s.idx_done, s.st));
+                s.idx_pending = true;
+            } else {
+                CK(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+            }
             CK(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
         }
         // the kernel indexes indices/data with the absolute offsets of h_indptr: shift the bases
-        rc = aucell_csr_f32(p, d_indptr, d_indices - e0, d_vals - e0, nc, d_auc, d_nnz, s.st);
+        if (idx16)
+            rc = aucell_csr16_f32(p, d_indptr, reinterpret_cast<uint16_t*>(d_indices) - e0, d_vals - e0, nc, d_auc,
+                                  d_nnz, s.st);
+        else
+            rc = aucell_csr_f32(p, d_indptr, d_indices - e0, d_vals - e0, nc, d_auc, d_nnz, s.st);
         if (rc) break;
+        // a host that narrows slower than the link moves the int32 indices it saves (busy or few cores) is better off
+        // with the plain upload: ~6.5 G entries/s is what the 8-byte-per-entry path sustains on PCIe 5 x16
+        if (idx16 && !idx16_forced && narrow_chunks == 3 && narrow_n > (1 << 22) && narrow_ns > (double)narrow_n / 6.5)
+            idx16 = false;
         CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
         if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }

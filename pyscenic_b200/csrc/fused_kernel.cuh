@@ -81,7 +81,7 @@ struct FusedArgs {
     const ValT* dense;                  // IN_DENSE
     int64_t row_stride;
     const int64_t* indptr;              // IN_CSR
-    const int32_t* indices;
+    const int32_t* indices;             // IN_CSR16: really const uint16_t*
     const ValT* data;
     int64_t n_cells;
     int n_genes;
@@ -358,7 +358,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     // upper bound of the explicit entries: the row length.  Short rows are sorted in shared memory (the storage of
     // the fast path's histograms and bucket arrays), long ones in global scratch.
     int64_t bound = a.n_genes;
-    if (IN == IN_CSR) bound = a.indptr[cell + 1] - a.indptr[cell];
+    if (IN != IN_DENSE) bound = a.indptr[cell + 1] - a.indptr[cell];
     KeyT* lk;
     PosT* lp;
     if (bound <= a.gen_cap) {
@@ -372,7 +372,8 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     __syncthreads();
     int64_t count;
     const ValT* vals;
-    const int32_t* cols = nullptr;
+    using IdxT = typename IdxOf<IN>::type;
+    const IdxT* cols = nullptr;
     if (IN == IN_DENSE) {
         count = a.n_genes;
         vals = a.dense + cell * a.row_stride;
@@ -380,7 +381,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
         const int64_t begin = a.indptr[cell];
         count = a.indptr[cell + 1] - begin;
         vals = a.data + begin;
-        cols = a.indices + begin;
+        cols = reinterpret_cast<const IdxT*>(a.indices) + begin;
     }
     for (int64_t base = 0; base < count; base += NT) {
         const int64_t i = base + tid;
@@ -400,7 +401,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
             if (pred) {
                 const int idx = wbase + __popc(mk & lanemask_lt());
-                const int g = (IN == IN_DENSE) ? (int)i : cols[i];
+                const int g = (IN == IN_DENSE) ? (int)i : (int)cols[i];
                 lk[idx] = key;
                 lp[idx] = static_cast<const PosT*>(a.inv_perm)[g];
             }
@@ -507,17 +508,17 @@ __device__ __forceinline__ void for_slots(int nk, F&& f) {
 }
 
 // ---- row access ---------------------------------------------------------------------------------------------
-template <typename ValT>
+template <typename ValT, typename IdxT = int32_t>
 struct RowView {
     const ValT* vals;
-    const int32_t* cols;     // nullptr for dense rows (column == index)
+    const IdxT* cols;        // nullptr for dense rows (column == index)
     int count;               // stored entries (CSR) or n_genes (dense)
 };
 
 // Visit every element of a row with all threads in lock step (uniform trip count, so `f` may use warp votes):
 // f(is_explicit, key, column).  Dense rows are read with 128-bit loads over their 16-byte aligned interior.
-template <int NT = kF, typename ValT, typename F>
-__device__ __forceinline__ void stream_row(const RowView<ValT>& row, F f) {
+template <int NT = kF, typename ValT, typename IdxT, typename F>
+__device__ __forceinline__ void stream_row(const RowView<ValT, IdxT>& row, F f) {
     using KT = KeyOf<ValT>;
     using KeyT = typename KT::type;
     const int tid = (int)threadIdx.x;
@@ -528,7 +529,7 @@ __device__ __forceinline__ void stream_row(const RowView<ValT>& row, F f) {
             int col = 0;
             if (i < row.count) {
                 key = KT::make(row.vals[i]);
-                col = row.cols[i];
+                col = (int)row.cols[i];
             }
             f(key != KT::KEY_ZERO, key, col);
         }
@@ -570,8 +571,8 @@ __device__ __forceinline__ void stream_row(const RowView<ValT>& row, F f) {
 
 // Dense rows, one 128-bit vector per call: f(keys[V], first column).  Elements that do not exist (ragged head / tail,
 // threads past the end) are KEY_ZERO.  Uniform trip count, so `f` may use warp votes.
-template <int NT = kF, typename ValT, typename F>
-__device__ __forceinline__ void stream_dense_vec(const RowView<ValT>& row, F f) {
+template <int NT = kF, typename ValT, typename IdxT, typename F>
+__device__ __forceinline__ void stream_dense_vec(const RowView<ValT, IdxT>& row, F f) {
     using KT = KeyOf<ValT>;
     using KeyT = typename KT::type;
     const int tid = (int)threadIdx.x;
@@ -658,11 +659,12 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     __syncthreads();
 
     for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
-        RowView<ValT> row;
-        if (IN == IN_CSR) {
+        using IdxT = typename IdxOf<IN>::type;
+        RowView<ValT, IdxT> row;
+        if (IN != IN_DENSE) {
             const int64_t begin = a.indptr[cell];
             row.vals = a.data + begin;
-            row.cols = a.indices + begin;
+            row.cols = reinterpret_cast<const IdxT*>(a.indices) + begin;
             row.count = (int)(a.indptr[cell + 1] - begin);
         } else {
             row.vals = a.dense + cell * a.row_stride;
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         int why = 1;                      // reason code for the general path (statistics only)
         int c_exp = 0, c_pos = 0;         // this thread's explicit / positive entries
         KeyT kmin = KT::KEY_ZERO, kmax = 0;
-        if (IN == IN_CSR) {
+        if (IN != IN_DENSE) {
             direct = row.count <= kCapF;
             if (direct) {
                 nk = (row.count + kF - 1) / kF;
@@ -693,7 +695,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 for_slots<kItems>(nk, [&](auto K) {
                     constexpr int k = decltype(K)::value;
                     const int i = k * kF + tid;
-                    if (i < row.count) { v[k] = row.vals[i]; c[k] = row.cols[i]; }
+                    if (i < row.count) { v[k] = row.vals[i]; c[k] = (int)row.cols[i]; }
                 });
                 for_slots<kItems>(nk, [&](auto K) {
                     constexpr int k = decltype(K)::value;
@@ -758,7 +760,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         }
         // ---------------- cell statistics: #explicit, #positive, key range of the positives --------------------
         if (direct) {
-            if (IN == IN_CSR) {
+            if (IN != IN_DENSE) {
                 for_slots<kItems>(nk, [&](auto K) {       // branch-free: zeros / negatives never lower kmin
                     constexpr int k = decltype(K)::value;
                     const bool ps = key[k] < KT::KEY_ZERO;
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                     kmax = tmax(kmax, ps ? key[k] : (KeyT)0);
                 });
             }
-        } else if (IN == IN_CSR) {
+        } else if (IN != IN_DENSE) {
             stream_row(row, [&](bool ex, KeyT kk, int) {
                 if (ex) {
                     ++c_exp;

@@ -96,6 +96,10 @@ struct aucell_plan {
         cudaStream_t st = nullptr;
         char* buf = nullptr;       // one allocation: indptr | indices | values | auc | nnz
         size_t bytes = 0;
+        uint16_t* pin_idx = nullptr;   // pinned host staging of a chunk's column indices narrowed to uint16
+        size_t pin_bytes = 0;
+        cudaEvent_t idx_done = nullptr;   // the upload out of pin_idx has finished
+        bool idx_pending = false;
     };
     mutable std::mutex host_mu;
     mutable std::vector<HostSlot> host_slots;
@@ -212,7 +216,8 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     if (n_cells == 0) return AUCELL_OK;
     if (IN == IN_DENSE && (!dense || row_stride < p->n_genes))
         return fail(AUCELL_ERR_INVALID, "dense input: NULL pointer or row_stride < n_genes");
-    if (IN == IN_CSR && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (IN != IN_DENSE && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
+    if (IN == IN_CSR16 && !p->pos16) return fail(AUCELL_ERR_INVALID, "uint16 column indices need n_genes <= 65535");
     if (!out_auc) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
@@ -265,8 +270,12 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
-    if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
-    return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+    if constexpr (IN == IN_CSR16) {       // 16-bit indices imply 16-bit positions: one instantiation
+        return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, false);
+    } else {
+        if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+        return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+    }
 }
 
 // create_rankings through the fused kernel in RANKS mode (bucket-sort ranking of every gene).

@@ -274,14 +274,19 @@ class AUCellPlan:
         return out
 
     def aucell_csr(self, indptr, indices, data, out=None, out_nnz=None, stream=None):
-        """indptr int64 [n_cells+1], indices int32 [nnz], data f32/f64 [nnz] CUDA tensors."""
+        """indptr int64 [n_cells+1], indices int32 (or uint16 with f32 data) [nnz], data f32/f64 [nnz] CUDA tensors."""
         import torch
 
-        assert indptr.is_cuda and indptr.dtype == torch.int64 and indices.dtype == torch.int32
+        assert indptr.is_cuda and indptr.dtype == torch.int64
         n_cells = indptr.numel() - 1
         if out is None:
             out = torch.empty((n_cells, self.n_regulons), dtype=torch.float64, device=indptr.device)
-        fn = self._csr_fn(data, "aucell")
+        if indices.dtype in (torch.uint16, torch.int16):        # 16-bit column indices (n_genes <= 65535, float32 data)
+            assert data.dtype == torch.float32
+            fn = self._lib.aucell_csr16_f32
+        else:
+            assert indices.dtype == torch.int32
+            fn = self._csr_fn(data, "aucell")
         _native.check(
             fn(self._handle, indptr.data_ptr(), indices.data_ptr(), data.data_ptr(), n_cells, out.data_ptr(),
                _torch_ptr(out_nnz), self._stream_ptr(stream))

@@ -459,6 +459,43 @@ def test_config3_full_size_properties_and_spot_check():
     assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))
 
 
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_uint16_column_indices_device_and_host_paths(unweighted, monkeypatch):
+    """aucell_csr16_f32 (uint16 column indices) and the host pipeline that narrows int32 indices on the fly must give
+    the bits of the int32 path; select-mode rows (> 4096 entries), empty rows and an out-of-range index included."""
+    import torch
+
+    n_cells, n_genes = 3000, 30000
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1800, seed=31, device="cuda", sigma=0.9)
+    ip = indptr.cpu().numpy()
+    assert (np.diff(ip) > 4096).any() and (np.diff(ip) < 1499).any()
+    rs = np.random.RandomState(15)
+    reg = synth.make_regulons(rs, n_genes, 120, 10, 400, weighted=not unweighted, repressors=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(42).permutation(n_genes)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        ref = plan.aucell_csr(indptr, indices, data)
+        got16 = plan.aucell_csr(indptr, indices.to(torch.uint16), data)
+        assert torch.equal(ref, got16)
+        hi, hx, hd = ip, indices.cpu().numpy(), data.cpu().numpy()
+        monkeypatch.setenv("AUCELL_B200_HOST_IDX16", "1")
+        monkeypatch.setenv("AUCELL_B200_HOST_THREADS", "3")
+        h16, nnz16 = plan.aucell_csr_host(hi, hx, hd, want_nnz=True, chunk_cells=257)
+        monkeypatch.setenv("AUCELL_B200_HOST_IDX16", "0")
+        h32, nnz32 = plan.aucell_csr_host(hi, hx, hd, want_nnz=True, chunk_cells=257)
+        assert np.array_equal(h16, ref.cpu().numpy()) and np.array_equal(h32, h16) and np.array_equal(nnz16, nnz32)
+        # a chunk large enough for the multi-threaded conversion, default chunking
+        monkeypatch.setenv("AUCELL_B200_HOST_IDX16", "1")
+        assert np.array_equal(plan.aucell_csr_host(hi, hx, hd), h16)
+        # an index that does not fit 16 bits is refused, not truncated
+        bad = hx.copy()
+        bad[len(bad) // 2] = 70000
+        with pytest.raises(Exception, match="out of range"):
+            plan.aucell_csr_host(hi, bad, hd)
+    X = synth.csr_to_dense(ip, indices.cpu().numpy(), data.cpu().numpy(), n_genes, 0, 64)
+    assert_auc_close(h16[:64], oracle_auc(X, perm, reg, cutoff))
+
+
 @pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.05, True), (0.97, True)])
 def test_fused_more_than_65535_genes(thr, unweighted):
     """n_genes > 65535: 32-bit positions; thr 0.97 pushes the cutoff above 65535, where unit-weight sums no longer fit
