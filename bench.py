@@ -327,8 +327,11 @@ def run_ours(args, rank, world, local_rank):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        moved_h2d, moved_d2h = plan.last_host_bytes()      # what the call really sent (uint16 indices when they fit)
         e2e = {"value": world * n_e2e * e2e_steps / float(tt.item()), "unit": "cells/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "cells_per_step_per_gpu": n_e2e,
+               "h2d_bytes_per_step": int(moved_h2d), "d2h_bytes_per_step": int(moved_d2h),
+               "host_input_bytes_per_step": int(h2d), "host_output_bytes_per_step": int(d2h),
+               "cells_per_step_per_gpu": n_e2e,
                "steps": e2e_steps, "timer": "host wall clock around the blocking C-ABI call, max over ranks"}
         # the device-resident and the host-buffer paths must agree bit for bit
         same = bool(torch.equal(h_out.to(dev), out[:n_e2e]))

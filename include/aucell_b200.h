@@ -145,6 +145,10 @@ int aucell_rss_f64(int device, const double* d_auc, int64_t n_cells, int64_t row
                    const int32_t* d_labels, int32_t n_types, const int64_t* h_type_counts, double* d_out, void* stream);
 
 /* ---- instrumentation -------------------------------------------------------------------------------- */
+/* Bytes the last aucell_*_host call on this plan moved over PCIe: out2 = { host-to-device, device-to-host }.  (The CSR
+ * call uploads uint16 column indices when n_genes <= 65535, so this can be less than the size of the caller's arrays.) */
+int aucell_plan_last_host_bytes(const aucell_plan_t* plan, int64_t* out2);
+
 /* Which code path the fused kernel took, summed over every call on this plan since the last reset (synchronises
  * the device): out5 = { cells, general path: more than 4096 explicit entries, general path: negative values ranked
  * below the cutoff, general path: crowded value bin, cells that needed zeros below the cutoff }. */

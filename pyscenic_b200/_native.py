@@ -57,6 +57,7 @@ EXPORTED_SYMBOLS = [
     "aucell_dense_f32_host",
     "aucell_b200_launch_count",
     "aucell_plan_path_stats",
+    "aucell_plan_last_host_bytes",
     "aucell_rss_f64",
 ]
 
@@ -155,6 +156,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_plan_create.restype = c_int
         lib.aucell_plan_path_stats.argtypes = [p, p, c_int]
         lib.aucell_plan_path_stats.restype = c_int
+        lib.aucell_plan_last_host_bytes.argtypes = [p, p]
+        lib.aucell_plan_last_host_bytes.restype = c_int
         lib.aucell_rss_f64.argtypes = [c_int, p, i64, i64, i32, p, i32, p, p, p]
         lib.aucell_rss_f64.restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]

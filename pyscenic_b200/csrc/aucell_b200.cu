@@ -302,6 +302,14 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     return AUCELL_OK;
 }
 
+int aucell_plan_last_host_bytes(const aucell_plan_t* p, int64_t* out2) {
+    if (!p || !out2) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> host_lock(p->host_mu);
+    out2[0] = p->last_h2d_bytes;
+    out2[1] = p->last_d2h_bytes;
+    return AUCELL_OK;
+}
+
 int aucell_plan_path_stats(const aucell_plan_t* p, uint64_t* out5, int reset) {
     if (!p || !out5) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
@@ -530,6 +538,7 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     int rc = ensure_host_slots(p, bytes, idx16 ? sizeof(uint16_t) * (size_t)max_nnz : 0);
     if (rc) return rc;
     int k = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
         aucell_plan::HostSlot& s = p->host_slots[k];
         int64_t* d_indptr = reinterpret_cast<int64_t*>(s.buf + o_indptr);
@@ -542,6 +551,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
         CK(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
+        h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1) + ne * (int64_t)(sizeof(float) + (idx16 ? 2 : 4));
+        d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         if (ne > 0) {
             if (idx16) {
                 if (s.idx_pending) CK(cudaEventSynchronize(s.idx_done));      // staging buffer free again
@@ -580,6 +591,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
     }
+    p->last_h2d_bytes = h2d_bytes;
+    p->last_d2h_bytes = d2h_bytes;
     return rc;
 }
 
@@ -604,6 +617,8 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
     int rc = ensure_host_slots(p, bytes);
     if (rc) return rc;
     int k = 0;
+    p->last_h2d_bytes = 0;
+    p->last_d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
         const aucell_plan::HostSlot& s = p->host_slots[k];
         float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
@@ -611,6 +626,8 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
         int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
         const int64_t nc = std::min(n_cells, c0 + chunk_cells) - c0;
         CK(cudaMemcpyAsync(d_vals, h_expr + c0 * row_stride, sizeof(float) * nc * row_stride, cudaMemcpyHostToDevice, s.st));
+        p->last_h2d_bytes += (int64_t)sizeof(float) * nc * row_stride;
+        p->last_d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         rc = aucell_dense_f32(p, d_vals, nc, row_stride, d_auc, d_nnz, s.st);
         if (rc) break;
         CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));

@@ -102,6 +102,7 @@ struct aucell_plan {
         bool idx_pending = false;
     };
     mutable std::mutex host_mu;
+    mutable int64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // what the last host-buffer call moved over PCIe
     mutable std::vector<HostSlot> host_slots;
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;

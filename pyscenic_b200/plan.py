@@ -208,6 +208,12 @@ class AUCellPlan:
         keys = ("cells", "general_too_many_entries", "general_negatives", "general_crowded_bin", "cells_with_zeros")
         return dict(zip(keys, [int(x) for x in buf]))
 
+    def last_host_bytes(self):
+        """(host-to-device, device-to-host) bytes the last ``*_host`` call moved (see aucell_plan_last_host_bytes)."""
+        buf = (ctypes.c_int64 * 2)()
+        _native.check(self._lib.aucell_plan_last_host_bytes(self._handle, buf))
+        return int(buf[0]), int(buf[1])
+
     # ------------------------------------------------------------------ host buffers (library streams chunks)
     def aucell_dense_host(self, values: np.ndarray, want_nnz: bool = False, chunk_cells: int = 0):
         v = np.ascontiguousarray(values, dtype=np.float32)
