@@ -477,7 +477,11 @@ bool narrow_indices(const int32_t* src, uint16_t* dst, int64_t n, int threads) {
     const int64_t per = ((n + threads - 1) / threads + 63) & ~int64_t(63);
     for (int t = 1; t < threads; ++t) {
         const int64_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
-        pool.emplace_back([&bad, src, dst, t, b, e]() { bad[(size_t)t] = narrow_span(src + b, dst + b, e - b); });
+        try {
+            pool.emplace_back([&bad, src, dst, t, b, e]() { bad[(size_t)t] = narrow_span(src + b, dst + b, e - b); });
+        } catch (...) {               // no more threads to be had (container limits): do the span here
+            bad[(size_t)t] = narrow_span(src + b, dst + b, e - b);
+        }
     }
     bad[0] = narrow_span(src, dst, std::min(n, per));
     for (auto& th : pool) th.join();
