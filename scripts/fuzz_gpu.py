@@ -58,6 +58,13 @@ while time.time() < t_end:
     with AUCellPlan(n_genes, perm, tables) as plan:
         got_d = plan.aucell_dense(cuda(X)).cpu().numpy()
         got_s = plan.aucell_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.int32)), cuda(csr.data)).cpu().numpy()
+        if not use64:     # uint16 column indices (device entry point) and the host pipelines (int32 kept / narrowed)
+            got_16 = plan.aucell_csr(cuda(csr.indptr.astype(np.int64)), cuda(csr.indices.astype(np.uint16)), cuda(csr.data)).cpu().numpy()
+            got_h = plan.aucell_csr_host(csr.indptr.astype(np.int64), csr.indices.astype(np.int32), csr.data, chunk_cells=int(rs.randint(1, 9)))
+            got_hd = plan.aucell_dense_host(X, chunk_cells=int(rs.randint(1, 9)))
+            assert np.array_equal(got_16, got_s), ("csr16 vs csr", it, n_genes, kind, dens, thr, R)
+            assert np.array_equal(got_h, got_s), ("csr host vs csr", it, n_genes, kind, dens, thr, R)
+            assert np.array_equal(got_hd, got_s), ("dense host vs csr", it, n_genes, kind, dens, thr, R)
     with AUCellPlan(n_genes, None, synth.regulon_tables_from_arrays(names, indptr, inv[genes].astype(np.int32), weights, n_genes=n_genes, rank_cutoff=cutoff, unweighted=unweighted)) as plan4r:
         got_4r = plan4r.from_rankings(cuda(want_r.view(np.int32))).cpu().numpy()
     assert np.array_equal(got_d, got_s), ("dense vs csr", it, n_genes, kind, dens, thr, R)
