@@ -1,6 +1,6 @@
 // launch.cuh -- plan object, error helpers and the kernel launchers shared by the translation units of
-// libaucell_b200.so (aucell_b200.cu: C-ABI + float32 kernels; aucell_f64.cu: float64 kernels).  Splitting the
-// instantiations lets the two halves compile in parallel.
+// libaucell_b200.so: aucell_b200.cu (C-ABI, plan, host pipelines) and one unit per input kind / dtype
+// (aucell_{f32,f64}_{dense,csr}.cu, aucell_f32_csr16.cu) so that the kernel instantiations compile in parallel.
 #pragma once
 #include "aucell_b200.h"
 
