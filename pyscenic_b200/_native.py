@@ -83,21 +83,60 @@ def _nvcc() -> Optional[str]:
     return None
 
 
+_HASH_PATH = LIB_PATH + ".src.sha256"
+_LOCK_PATH = LIB_PATH + ".lock"
+
+
+def _source_hash() -> str:
+    """sha256 over the sources and the compiler flags the library is built from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + TRANSLATION_UNITS).encode())
+    for path in _sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
+    """The library is rebuilt when the sources it was built from changed.  The decision is made on CONTENT (a hash
+    written next to the library by build()), not on modification times: the library travels to other machines by
+    file copy, which does not keep mtimes in order, and N ranks of one job must not all decide to rebuild."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    if os.path.exists(_HASH_PATH):
+        with open(_HASH_PATH) as fh:
+            return fh.read().strip() != _source_hash()
+    t = os.path.getmtime(LIB_PATH)          # library built by hand (no hash file): fall back to mtimes
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library for sm_100a in-tree.  Cross-compiles without a GPU.  The translation units are
-    compiled concurrently (object files under pyscenic_b200/build/) and linked with ``nvcc -shared``."""
+    compiled concurrently (object files under pyscenic_b200/build/) and linked with ``nvcc -shared``.  Safe to call
+    from several processes at once (ranks of one job): a file lock serialises them and the late-comers find the
+    library up to date."""
+    import fcntl
+
     if not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build {} (set NVCC or add nvcc to PATH)".format(LIB_NAME))
+    with open(_LOCK_PATH, "w") as lock_fh:
+        fcntl.flock(lock_fh, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():      # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock_fh, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc: str, verbose: bool) -> str:
+    src_hash = _source_hash()
     obj_dir = os.path.join(_PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
@@ -114,11 +153,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(out)
         objs.append(obj)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH + ".tmp"] + objs
+    tmp = "{}.tmp.{}".format(LIB_PATH, os.getpid())
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n{}\n{}".format(" ".join(link), res.stdout))
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(tmp, LIB_PATH)
+    with open(_HASH_PATH + ".tmp", "w") as fh:
+        fh.write(src_hash + "\n")
+    os.replace(_HASH_PATH + ".tmp", _HASH_PATH)
     return LIB_PATH
 
 

@@ -180,3 +180,53 @@ def test_reference_gmt_fixture_loads():
     assert len(gs) == 189
     assert min(len(s) for s in gs) == 10 and max(len(s) for s in gs) == 481
     assert sum(len(s) for s in gs) == 31319
+
+
+def _build_worker(args):
+    """One rank of a multi-process job asking for the library (fork: inherits the patched module state)."""
+    from pyscenic_b200 import _native
+
+    _native.build()
+    return os.getpid()
+
+
+def test_concurrent_builds_are_serialised_and_decided_by_content(tmp_path, monkeypatch):
+    """N ranks of one job must not all rebuild the library (seen on an 8-GPU box: every rank found the copied library
+    'older' than a source file and raced on the link step).  Staleness is a content hash; builds take a file lock and
+    late-comers find the work done."""
+    import multiprocessing as mp
+    import time
+
+    from pyscenic_b200 import _native
+
+    lib = str(tmp_path / "libfake.so")
+    counter = tmp_path / "builds.txt"
+    monkeypatch.setattr(_native, "LIB_PATH", lib)
+    monkeypatch.setattr(_native, "_HASH_PATH", lib + ".src.sha256")
+    monkeypatch.setattr(_native, "_LOCK_PATH", lib + ".lock")
+    monkeypatch.setattr(_native, "_nvcc", lambda: "/bin/true")
+
+    def fake_build(nvcc, verbose):
+        time.sleep(0.3)
+        with open(counter, "a") as fh:
+            fh.write("built by %d\n" % os.getpid())
+        with open(lib, "wb") as fh:
+            fh.write(b"\x7fELF")
+        with open(lib + ".src.sha256", "w") as fh:
+            fh.write(_native._source_hash() + "\n")
+        return lib
+
+    monkeypatch.setattr(_native, "_build_locked", fake_build)
+    assert _native.is_stale()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(4) as pool:
+        pids = pool.map(_build_worker, range(4))
+    assert len(set(pids)) >= 2
+    assert counter.read_text().count("built by") == 1
+    assert not _native.is_stale()
+    # a copy that scrambles modification times does not trigger a rebuild; a changed source does
+    os.utime(lib, (1, 1))
+    assert not _native.is_stale()
+    with open(lib + ".src.sha256", "w") as fh:
+        fh.write("0" * 64 + "\n")
+    assert _native.is_stale()
