@@ -493,8 +493,12 @@ bool narrow_indices(const int32_t* src, uint16_t* dst, int64_t n, int threads) {
 int host_threads() {
     const char* env = getenv("AUCELL_B200_HOST_THREADS");
     if (env && *env) return std::max(1, std::min(64, atoi(env)));
-    const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(16u, hw ? hw : 4u));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    // ranks of one job on this host share its cores (torchrun exports LOCAL_WORLD_SIZE)
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 1) hw = std::max(1u, hw / (unsigned)atoi(lws));
+    return (int)std::max(1u, std::min(16u, hw));
 }
 
 }  // namespace
@@ -538,6 +542,9 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     double narrow_ns = 0.0;               // time spent narrowing and entries narrowed so far in this call
     int64_t narrow_n = 0;
     int narrow_chunks = 0;
+    int chunk_no = 0;                     // pipeline rate once the slots are full: entries enqueued per second
+    int64_t rate_n = 0;
+    std::chrono::steady_clock::time_point rate_t0;
     const int n_threads = idx16 ? host_threads() : 1;
     int rc = ensure_host_slots(p, bytes, idx16 ? sizeof(uint16_t) * (size_t)max_nnz : 0);
     if (rc) return rc;
@@ -588,6 +595,16 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         // with the plain upload: ~6.5 G entries/s is what the 8-byte-per-entry path sustains on PCIe 5 x16
         if (idx16 && !idx16_forced && narrow_chunks == 3 && narrow_n > (1 << 22) && narrow_ns > (double)narrow_n / 6.5)
             idx16 = false;
+        // ... and when the pipeline as a whole runs well below what the link carries (several GPUs behind one host
+        // memory system: measured 8 ranks on 32 cores), narrowing only adds host memory traffic: stop it.  The enqueue
+        // loop is throttled by the slots, so its period is the pipeline's.
+        ++chunk_no;
+        if (chunk_no == kHostSlots) rate_t0 = std::chrono::steady_clock::now();
+        if (chunk_no > kHostSlots) rate_n += ne;
+        if (idx16 && !idx16_forced && chunk_no == 3 * kHostSlots && rate_n > (1 << 24)) {
+            const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - rate_t0).count();
+            if (ns > (double)rate_n / 4.5) idx16 = false;        // < 4.5 G entries/s
+        }
         CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
         if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
