@@ -305,7 +305,8 @@ struct ScatterRange {
             int at = incl - mine_n;
 #pragma unroll
             for (int k = LO; k < HI; ++k) {
-                for (uint32_t i = 0; i < tc[k]; ++i) {
+#pragma unroll 1
+                for (uint32_t i = 0; i < tc[k]; ++i) {          // a gene sits in ~2 regulons: keep the loop rolled
                     qj[at] = tb[k] + i;
                     qm[at] = (PosT)mv[k];
                     ++at;
@@ -963,6 +964,8 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             const uint32_t b = h2[sb], e = h2[sb + 1];
                             const unsigned long long mine = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)pos[k];
                             uint32_t rank = b;
+                            // sub-buckets hold ~1 entry: a plain loop beats the 8/4/2/1 unrolling ladder
+#pragma unroll 1
                             for (uint32_t j = b; j < e; ++j) rank += store.before(j, key[k], pos[k], mine);
                             if (RANKS) {
                                 a.out_rank[cell * (int64_t)n_genes + (unsigned)pos[k]] = rank;
