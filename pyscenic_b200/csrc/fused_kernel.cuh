@@ -160,6 +160,7 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
     const uint32_t b = __ldg(t.tptr + p), e = __ldg(t.tptr + p + 1);
     if (ACC64) {
         if (t.tent != nullptr) {
+#pragma unroll 1
             for (uint32_t j = b; j < e; ++j) {
                 const unsigned long long ent = __ldg(t.tent + j);
                 const uint32_t r = (uint32_t)(ent & 0xFFFFull);
@@ -172,6 +173,7 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
                 if (hi) atomicAdd(&acc_hi[r], hi);
             }
         } else {  // unit weights but a cutoff too large for 32-bit sums
+#pragma unroll 1
             for (uint32_t j = b; j < e; ++j) {
                 const uint32_t r = __ldg(t.tacc16 + j);
                 const uint32_t old = atomicAdd(&acc_lo[r], mval);
@@ -179,6 +181,7 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
             }
         }
     } else {
+#pragma unroll 1
         for (uint32_t j = b; j < e; ++j) atomicAdd(&acc_lo[__ldg(t.tacc16 + j)], mval);
     }
 }
@@ -319,6 +322,7 @@ struct ScatterRange {
             ScatterRange<ACC64, PosT, NI, QCAP, LO, (LO + HI) / 2>::run(t, acc_lo, acc_hi, qj, qm, tb, tc, mv, lane);
             ScatterRange<ACC64, PosT, NI, QCAP, (LO + HI) / 2, HI>::run(t, acc_lo, acc_hi, qj, qm, tb, tc, mv, lane);
         } else {                          // one slot alone overflows the queue (genes in hundreds of regulons)
+#pragma unroll 1
             for (uint32_t i = 0; i < tc[LO]; ++i) apply_entry<ACC64>(t, acc_lo, acc_hi, tb[LO] + i, mv[LO]);
         }
     }
@@ -896,6 +900,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             }
             if (!general) {
                 // S3: clear level-2 histogram (rep is dead: its last readers finished before the barriers above)
+#pragma unroll 1
                 for (int b = tid; b <= n_s; b += kF) h2[b] = 0u;
                 __syncthreads();
                 // S4: level-2 histogram
@@ -931,9 +936,11 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         const int per = (n_s + kF - 1) / kF;
                         const int b0 = tid * per, b1 = min(b0 + per, n_s);
                         int local = 0;
+#pragma unroll 1
                         for (int b = b0; b < b1; ++b) local += (int)h2[b];
                         int total;
                         int run = block_excl_scan_n<kF, false>(local, s_scan2, total);
+#pragma unroll 1
                         for (int b = b0; b < b1; ++b) {
                             const int c = (int)h2[b];
                             h2[b] = (uint32_t)run;
@@ -989,6 +996,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -----------------------------
             const int q_zero = cutoff - n_gt;
             if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
+#pragma unroll 1
             for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
             __syncthreads();
             if (direct) {
@@ -1007,14 +1015,17 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             const int per = (a.n_words + kF - 1) / kF;
             const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
             int local = 0;
+#pragma unroll 1
             for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
             int total;
             int run = block_excl_scan_n<kF>(local, s_scan, total);
+#pragma unroll 1
             for (int w = w0; w < w1; ++w) {
                 s_wpre[w] = (uint32_t)run;
                 run += __popc(s_bits[w]);
             }
             __syncthreads();
+#pragma unroll 1
             for (int p = tid; p < n_genes; p += kF) {
                 const int w = p >> 5;
                 const uint32_t bw = s_bits[w];
