@@ -243,6 +243,7 @@ __device__ __forceinline__ void flush_queue(const GeneTableDev& t, uint32_t* __r
     __syncwarp();
     const int lane = threadIdx.x & 31;
     constexpr int U = 4;
+#pragma unroll 1
     for (int base = 0; base < qn; base += 32 * U) {
         unsigned long long ent[U];
         unsigned mval[U];
@@ -791,6 +792,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
             s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
         }
+#pragma unroll 1
         for (int b = tid; b <= kNb1; b += kF) h1[b] = 0u;     // clear the level-1 histogram while we are at it
         if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
         if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0x7FFFFFFF; s_cnt[1] = 0; }
