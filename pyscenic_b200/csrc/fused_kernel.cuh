@@ -158,9 +158,10 @@ template <bool ACC64>
 __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* __restrict__ acc_lo,
                                                uint32_t* __restrict__ acc_hi, unsigned p, unsigned mval) {
     const uint32_t b = __ldg(t.tptr + p), e = __ldg(t.tptr + p + 1);
+    // (these row loops stay unrolled: the compiler batches the table loads of several entries, which is what
+    //  aucell_from_rankings_kernel lives on -- rolled, it runs at half the rate)
     if (ACC64) {
         if (t.tent != nullptr) {
-#pragma unroll 1
             for (uint32_t j = b; j < e; ++j) {
                 const unsigned long long ent = __ldg(t.tent + j);
                 const uint32_t r = (uint32_t)(ent & 0xFFFFull);
@@ -173,7 +174,6 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
                 if (hi) atomicAdd(&acc_hi[r], hi);
             }
         } else {  // unit weights but a cutoff too large for 32-bit sums
-#pragma unroll 1
             for (uint32_t j = b; j < e; ++j) {
                 const uint32_t r = __ldg(t.tacc16 + j);
                 const uint32_t old = atomicAdd(&acc_lo[r], mval);
@@ -181,7 +181,6 @@ __device__ __forceinline__ void scatter_packed(const GeneTableDev& t, uint32_t* 
             }
         }
     } else {
-#pragma unroll 1
         for (uint32_t j = b; j < e; ++j) atomicAdd(&acc_lo[__ldg(t.tacc16 + j)], mval);
     }
 }
