@@ -374,7 +374,7 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem = align16(p->n_acc * 8);
+    const int smem = align16(kHitCap * (int)sizeof(uint2) + p->n_acc * 8);     // hit list | accumulators
     if (smem > p->smem_optin) return fail(AUCELL_ERR_UNSUPPORTED, "too many regulons for the shared-memory accumulators");
     GeneTableDev reg = tab_of(p);
     if (p->acc64) {

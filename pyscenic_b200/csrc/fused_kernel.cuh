@@ -1447,15 +1447,26 @@ __global__ void __launch_bounds__(kS, 4) aucell_fused_sel_kernel(const FusedArgs
 
 // aucell4r path: AUCs from an existing ranking matrix (reference aucell.py:98-182; ctxcore auc2d): the same
 // scatter, driven straight from the ranking row (T is indexed by the ranking matrix' own columns).
+//
+// Only ~auc_threshold of a row's ranks lie below the cutoff, spread at random over the row.  Scattering them where
+// they are found leaves a warp waiting on one or two lanes' table rows at every step, so the hits are first collected
+// into a compact list in shared memory ((column, cutoff - rank), slots handed out per 128-bit vector with three warp
+// votes) and then applied one hit per thread with every lane busy.  Hits beyond the list's capacity (a row with more
+// ranks below the cutoff than a ranking has: arbitrary input) are applied where they are found.
+constexpr int kHitCap = 4096;             // (column, multiplier) pairs per cell in shared memory
+
 template <bool ACC64>
 __global__ void __launch_bounds__(kF) aucell_from_rankings_kernel(const uint32_t* __restrict__ rnk, int64_t n_cells,
                                                                   int64_t row_stride, int n_genes, int cutoff,
                                                                   GeneTableDev tab, double* __restrict__ out_auc) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem);
+    uint2* const hits = reinterpret_cast<uint2*>(smem);                       // [kHitCap]
+    uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem + kHitCap * sizeof(uint2));
     uint32_t* const acc_hi = acc_lo + tab.n_acc;
-    const int tid = threadIdx.x;
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 2 * tab.n_acc; i += kF) acc_lo[i] = 0u;
+    if (tid == 0) s_n = 0;
     __syncthreads();
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const uint32_t* row = rnk + cell * row_stride;
@@ -1468,19 +1479,47 @@ __global__ void __launch_bounds__(kF) aucell_from_rankings_kernel(const uint32_t
             if (r < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)tid, (uint32_t)cutoff - r);
         }
         const uint4* row4 = reinterpret_cast<const uint4*>(row + h);
-        for (int q = tid; q < n4; q += kF) {
-            const uint4 v = __ldg(row4 + q);
-            const int j = h + (q << 2);
-            if (v.x < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)j, (uint32_t)cutoff - v.x);
-            if (v.y < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 1), (uint32_t)cutoff - v.y);
-            if (v.z < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 2), (uint32_t)cutoff - v.z);
-            if (v.w < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)(j + 3), (uint32_t)cutoff - v.w);
+#pragma unroll 1
+        for (int base = 0; base < n4; base += kF) {          // uniform trip count: the body votes
+            const int q = base + tid;
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (q < n4) v = __ldg(row4 + q);
+            const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c += (r[k] < (uint32_t)cutoff) ? 1 : 0;
+            const unsigned b0 = __ballot_sync(0xffffffffu, c & 1);
+            const unsigned b1 = __ballot_sync(0xffffffffu, c & 2);
+            const unsigned b2 = __ballot_sync(0xffffffffu, c & 4);
+            if (b0 | b1 | b2) {
+                const unsigned lt = lanemask_lt();
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_n, __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                int idx = wbase + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                const unsigned j = (unsigned)(h + (q << 2));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (r[k] < (uint32_t)cutoff) {
+                        if (idx < kHitCap) hits[idx] = make_uint2(j + k, (uint32_t)cutoff - r[k]);
+                        else scatter_packed<ACC64>(tab, acc_lo, acc_hi, j + k, (uint32_t)cutoff - r[k]);
+                        ++idx;
+                    }
+                }
+            }
         }
         for (int j = h + (n4 << 2) + tid; j < n_genes; j += kF) {
             const uint32_t r = row[j];
             if (r < (uint32_t)cutoff) scatter_packed<ACC64>(tab, acc_lo, acc_hi, (unsigned)j, (uint32_t)cutoff - r);
         }
         __syncthreads();
+        const int n_hits = min(s_n, kHitCap);
+        for (int i = tid; i < n_hits; i += kF) {
+            const uint2 e = hits[i];
+            scatter_packed<ACC64>(tab, acc_lo, acc_hi, e.x, e.y);
+        }
+        __syncthreads();
+        if (tid == 0) s_n = 0;
         write_aucs_packed<ACC64, kF>(tab, acc_lo, acc_hi, out_auc + cell * (int64_t)tab.n_regulons);
         __syncthreads();
     }
