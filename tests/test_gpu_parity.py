@@ -459,6 +459,41 @@ def test_config3_full_size_properties_and_spot_check():
     assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))
 
 
+@pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.6, False), (0.6, True)])
+def test_from_rankings_hit_list_and_its_overflow(thr, unweighted):
+    """aucell4r kernel: ranks below the cutoff are collected into a 4,096-entry list before they are scattered; with
+    thr 0.6 of 12,001 genes a row holds 7,200 of them, so the overflow branch (scatter where found) runs too.  Rows at
+    every 16-byte misalignment (odd n_genes, row_stride > n_genes)."""
+    import torch
+
+    rs = np.random.RandomState(23)
+    n_cells, n_genes = 37, 12001
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.15)
+    perm = rs.permutation(n_genes)
+    ranks = O.create_rankings_c(X, perm)                       # [n_cells, n_genes] uint32, shuffled column order
+    cutoff = O.derive_rank_cutoff(thr, n_genes)
+    assert (thr > 0.5) == (cutoff > 4096)
+    names, indptr, genes, weights = synth.make_regulons(rs, n_genes, 90, 5, 600, weighted=True)
+    cols = [np.sort(genes[indptr[k]:indptr[k + 1]]) for k in range(len(names))]
+    ws = [np.ones(len(c)) if unweighted else weights[indptr[k]:indptr[k + 1]][np.argsort(genes[indptr[k]:indptr[k + 1]], kind="stable")]
+          for k, c in enumerate(cols)]
+    want = O.auc_matrix_from_ranks(ranks, cols, ws, [True] * len(names), cutoff)
+    tables = synth.regulon_tables_from_arrays(names, indptr, genes, weights, n_genes=n_genes, rank_cutoff=cutoff,
+                                              unweighted=unweighted)
+    from pyscenic_b200.plan import AUCellPlan
+
+    with AUCellPlan(n_genes, None, tables) as plan:            # identity permutation: columns are ranking columns
+        padded = torch.zeros((n_cells, n_genes + 3), dtype=torch.int32, device="cuda")
+        padded[:, :n_genes] = torch.from_numpy(ranks.view(np.int32)).cuda()
+        got = plan.from_rankings(padded[:, :n_genes]).cpu().numpy()
+        got2 = plan.from_rankings(torch.from_numpy(ranks.view(np.int32)).cuda()).cpu().numpy()
+    assert np.array_equal(got, got2)
+    if unweighted:
+        assert np.array_equal(got, want)
+    else:
+        assert_auc_close(got, want)
+
+
 @pytest.mark.parametrize("unweighted", [False, True])
 def test_uint16_column_indices_device_and_host_paths(unweighted, monkeypatch):
     """aucell_csr16_f32 (uint16 column indices) and the host pipeline that narrows int32 indices on the fly must give
