@@ -807,6 +807,78 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
         const int n_zero = n_genes - m;
         if (cutoff - n_gt - n_zero > 0) { general = true; why = 2; }   // negatives rank below the cutoff
 
+        // ---------------- ZEROS: implicit zeros fill ranks n_gt .. cutoff-1 in position order ---------------------
+        // (bitmap of the positions of explicit entries + prefix popcount).  AUC mode runs it after the scatter of the
+        // positives; RANKS mode (cutoff = n_genes: every zero gets a rank) runs it BEFORE the ranking, see below.
+        auto zeros_phase = [&]() {
+            const int q_zero = cutoff - n_gt;
+            if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
+#pragma unroll 1
+            for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
+            __syncthreads();
+            if (direct) {
+#pragma unroll
+                for (int k = 0; k < kItems; ++k)
+                    if (k < nk && key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
+            } else {
+                stream_row(row, [&](bool ex, KeyT, int col) {
+                    if (ex) {
+                        const unsigned p = (unsigned)__ldg(static_cast<const PosT*>(a.inv_perm) + col);
+                        atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+                    }
+                });
+            }
+            __syncthreads();
+            const int per = (a.n_words + kF - 1) / kF;
+            const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
+            int local = 0;
+#pragma unroll 1
+            for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
+            int total;
+            int run = block_excl_scan_n<kF>(local, s_scan, total);
+#pragma unroll 1
+            for (int w = w0; w < w1; ++w) {
+                s_wpre[w] = (uint32_t)run;
+                run += __popc(s_bits[w]);
+            }
+            __syncthreads();
+            if (RANKS) {
+                // every position gets n_gt + #zeros before it, four positions per 128-bit store; what lands on the
+                // positions of explicit entries is overwritten by their own ranks later (S7 / the general path run
+                // after this phase in RANKS mode, behind block barriers)
+                uint32_t* const orow = a.out_rank + cell * (int64_t)n_genes;
+                auto zrank = [&](int p) -> uint32_t {
+                    const int w = p >> 5;
+                    return (uint32_t)(n_gt + p - (int)s_wpre[w] - __popc(s_bits[w] & ((1u << (p & 31)) - 1u)));
+                };
+                const int oh = min(n_genes, (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(orow) & 15u)) & 15u) >> 2));
+                const int nq = (n_genes - oh) >> 2;
+                if (tid < oh) orow[tid] = zrank(tid);
+                uint4* const o4 = reinterpret_cast<uint4*>(orow + oh);
+#pragma unroll 1
+                for (int q = tid; q < nq; q += kF) {
+                    const int p = oh + (q << 2);
+                    o4[q] = make_uint4(zrank(p), zrank(p + 1), zrank(p + 2), zrank(p + 3));
+                }
+                for (int p = oh + (nq << 2) + tid; p < n_genes; p += kF) orow[p] = zrank(p);
+            } else {
+#pragma unroll 1
+                for (int p = tid; p < n_genes; p += kF) {
+                    const int w = p >> 5;
+                    const uint32_t bw = s_bits[w];
+                    const int z0 = (w << 5) - (int)s_wpre[w];
+                    if (z0 >= q_zero) break;
+                    if (!((bw >> (p & 31)) & 1u)) {
+                        const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
+                        if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
+                    }
+                }
+            }
+        };
+        if (RANKS && !general && n_gt < cutoff) {
+            zeros_phase();
+            __syncthreads();              // orders the vector stores above before the positives' own rank stores
+        }
         if (!general && n_gt > 0) {
             // ---------------- RANK: two-level bucket sort of the positives ------------------------------------
             const KeyT range = kmax - kmin;
@@ -993,52 +1065,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 }
             }
         }
-        if (!general && n_gt < cutoff) {
-            // ---------------- ZEROS: fill ranks n_gt .. cutoff-1 in position order -----------------------------
-            const int q_zero = cutoff - n_gt;
-            if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
-#pragma unroll 1
-            for (int w = tid; w < a.n_words; w += kF) s_bits[w] = 0u;
-            __syncthreads();
-            if (direct) {
-#pragma unroll
-                for (int k = 0; k < kItems; ++k)
-                    if (k < nk && key[k] != KT::KEY_ZERO) atomicOr(&s_bits[(unsigned)pos[k] >> 5], 1u << ((unsigned)pos[k] & 31));
-            } else {
-                stream_row(row, [&](bool ex, KeyT, int col) {
-                    if (ex) {
-                        const unsigned p = (unsigned)__ldg(static_cast<const PosT*>(a.inv_perm) + col);
-                        atomicOr(&s_bits[p >> 5], 1u << (p & 31));
-                    }
-                });
-            }
-            __syncthreads();
-            const int per = (a.n_words + kF - 1) / kF;
-            const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
-            int local = 0;
-#pragma unroll 1
-            for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
-            int total;
-            int run = block_excl_scan_n<kF>(local, s_scan, total);
-#pragma unroll 1
-            for (int w = w0; w < w1; ++w) {
-                s_wpre[w] = (uint32_t)run;
-                run += __popc(s_bits[w]);
-            }
-            __syncthreads();
-#pragma unroll 1
-            for (int p = tid; p < n_genes; p += kF) {
-                const int w = p >> 5;
-                const uint32_t bw = s_bits[w];
-                const int z0 = (w << 5) - (int)s_wpre[w];
-                if (z0 >= q_zero) break;
-                if (!((bw >> (p & 31)) & 1u)) {
-                    const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                    if (RANKS) a.out_rank[cell * (int64_t)n_genes + p] = (uint32_t)(n_gt + z);     // coalesced
-                    else if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
-                }
-            }
-        }
+        if (!RANKS && !general && n_gt < cutoff) zeros_phase();
         if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
         if (a.stats != nullptr && tid == 0) {
             atomicAdd(a.stats + 0, 1ull);
