@@ -987,11 +987,18 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         const uint32_t base = h1[bin];
                         if ((int)base < cutoff) {
                             const uint32_t c = h1[bin + 1] - base;
-                            uint32_t sub = 0;
+                            uint32_t sub;
                             if (!((mixed[bin >> 5] >> (bin & 31)) & 1u)) {
+                                // one key (tie class): split by shuffled position, ~1 entry per sub-bucket
                                 sub = (uint32_t)(((unsigned long long)((unsigned)pos[k]) * c * a.inv_ng) >> 32);
-                                sub = min(sub, c - 1u);
+                            } else {
+                                // several keys (continuous data): split by the key's offset inside the bin, 20 bits of
+                                // it -- monotone in the key, so sub-bucket order stays rank order
+                                const KeyT off = (KeyT)(key[k] - kmin) & (((KeyT)1 << shift) - 1);
+                                const uint32_t t20 = shift >= 20 ? (uint32_t)(off >> (shift - 20)) : (uint32_t)(off << (20 - shift));
+                                sub = (uint32_t)(((unsigned long long)t20 * c) >> 20);
                             }
+                            sub = min(sub, c - 1u);
                             const uint32_t sb = base + sub;
                             const uint32_t got = atomicAdd(&h2[sb], 1u);
                             if (got >= (uint32_t)kMaxSub) s_flag[0] = 1;

@@ -296,6 +296,11 @@ def test_fast_path_and_its_fallback(unweighted, fused_variant):
     X[7, idx[:100]] = rs.rand(100).astype(np.float32) + 1; X[7, idx[100:]] = 0.0   # 100 pos, 800 zeros, 5100 neg
     X[8] = rs.poisson(3.0, n_genes).astype(np.float32)                        # 95 % non-zero counts: long row, ties
     X[9] = 7.0                                                                # one value everywhere
+    # two adjacent float32 values, 450 genes each, sharing one value bin with nothing to tell them apart at the bin's
+    # resolution: a crowded sub-bucket whatever the split -> general sort
+    X[10] = 0.0; X[10, idx[:450]] = 1.0; X[10, idx[450:]] = np.nextafter(np.float32(1.0), np.float32(2.0)); X[10, idx[0]] = 1e6
+    X[11] = rs.randn(n_genes).astype(np.float32)                              # z-scored: all distinct, half negative
+    X[12] = rs.rand(n_genes).astype(np.float32) * (rs.rand(n_genes) < 0.3)     # uniform (0,1): many keys per value bin
     reg = synth.make_regulons(rs, n_genes, 50, 10, 400, weighted=True)
     perm = np.random.RandomState(5).permutation(n_genes)
     want = oracle_auc(X, perm, reg, cutoff, unweighted)
