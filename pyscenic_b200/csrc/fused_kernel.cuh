@@ -15,13 +15,15 @@
 //   RANK     positives are ranked by a two-level bucket sort on 32-bit shared atomics:
 //              level 1: value bins over the cell's own key range (ascending key = descending value);
 //                       bins starting at or beyond the cutoff are dropped;
-//              level 2: a bin with ONE distinct key (tie group) is split by shuffled position into as many
-//                       sub-buckets as it has entries (positions are uniform -> ~1 entry each); a bin with
-//                       several keys stays one sub-bucket;
+//              level 2: every kept bin is split into as many sub-buckets as it has entries -- a bin with ONE
+//                       distinct key (tie group) by shuffled position (positions are uniform -> ~1 entry each), a
+//                       bin with several keys (continuous data) by the key's offset inside the bin;
 //              exact:   entries are stored in sub-bucket order and each counts the members of its own sub-bucket
 //                       that sort before it:  rank = base2[sub] + count.
-//            Crowded sub-buckets (many distinct keys in one value bin), negatives ranked below the cutoff, or
-//            more entries than kF * kItems send the cell to the general path (bitonic sort in global scratch).
+//            Crowded sub-buckets (e.g. two adjacent values, hundreds of genes each, in one value bin), negatives
+//            ranked below the cutoff, or a selection of more than kF * kItems entries send the cell to the general
+//            path (bitonic sort in shared memory / global scratch).  Rows with more than kF * kItems explicit entries
+//            are streamed ("select mode") and only the bins that start below the cutoff come to registers.
 //   SCATTER  for each gene below the cutoff walk the gene-major regulon table T[pos] and add W * (cutoff - rank)
 //            into 64-bit integer accumulators in shared memory (32-bit atomics + carry; fixed-point weights).
 //            Integer adds commute, so the result does not depend on the order the atomics retire in.
@@ -1121,363 +1123,6 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     }
 }
 
-#ifdef AUCELL_B200_WITH_STREAMING
-// ---- the fused kernel, streaming variant --------------------------------------------------------------------
-// Same algorithm, organised so that registers only ever hold the entries that can rank below the cutoff:
-//   * 256 threads per CTA (4 CTAs resident per SM: four independent cells overlap each other's barriers and latencies);
-//   * the row is STREAMED three times (statistics, level-1 histogram, selection); it comes from HBM once and from L2
-//     afterwards.  Rows of any length and dense rows of any density stay on the fast path;
-//   * selection keeps the bins that start below the cutoff.  The bin that straddles the cutoff is usually one huge tie
-//     group (the lowest expressed value); when it holds a single key it is PRUNED by position: only its first
-//     S* = q + 8*sqrt(q) + 32 position sub-buckets are kept, q = cutoff - (entries in earlier bins).  Sub-buckets are
-//     equal slices of the shuffled position range, so the first S* of them contain ~S* entries; the kernel verifies
-//     that they contain at least q (else the cell takes the general path), which makes the pruning exact.
-// Measured SLOWER than aucell_fused_kernel in round 1 (15.0 vs 17.6 M cells/s; fewer instructions but 45 % issue-slot
-// utilisation), so it is not part of the default build: compile with -DAUCELL_B200_WITH_STREAMING and run with
-// AUCELL_B200_FUSED=streaming to A/B it (usable when rank_cutoff + 8*sqrt(rank_cutoff) + 96 <= kCapS).
-constexpr int kS = 256;
-constexpr int kSWarps = kS / 32;
-constexpr int kSItems = 8;
-constexpr int kCapS = kS * kSItems;      // 2048 kept entries per cell
-constexpr int kQS = kCapS / kSWarps;     // per-warp scatter queue: 256 items
-
-template <typename ValT, typename PosT, int IN, bool ACC64>
-__global__ void __launch_bounds__(kS, 4) aucell_fused_sel_kernel(const FusedArgs<ValT> a) {
-    using KT = KeyOf<ValT>;
-    using KeyT = typename KT::type;
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* const h1 = reinterpret_cast<uint32_t*>(smem + a.off_h1);      // [kNb1 + 1]
-    uint32_t* const h2 = reinterpret_cast<uint32_t*>(smem + a.off_h2);      // [kCapS + 1]
-    KeyT* const rep = reinterpret_cast<KeyT*>(smem + a.off_h2);             // [kNb1] alias of h2
-    KeyT* const fk = reinterpret_cast<KeyT*>(smem + a.off_fk);
-    PosT* const fp = reinterpret_cast<PosT*>(smem + a.off_fp);
-    uint32_t* const mixed = reinterpret_cast<uint32_t*>(smem + a.off_mixed);
-    uint32_t* const s_bits = reinterpret_cast<uint32_t*>(smem + a.off_bits);
-    uint32_t* const s_wpre = reinterpret_cast<uint32_t*>(smem + a.off_wpre);
-    uint32_t* const acc_lo = reinterpret_cast<uint32_t*>(smem + a.off_acc);
-    uint32_t* const acc_hi = acc_lo + a.tab.n_acc;
-    BucketStore<KeyT, PosT> store;
-    store.kp = reinterpret_cast<unsigned long long*>(smem + a.off_fk);
-    store.k = fk;
-    store.p = fp;
-    __shared__ int s_scan[33];
-    __shared__ int s_scan2[33];
-    __shared__ int s_cnt[2];
-    __shared__ int s_red_i[2][kSWarps];
-    __shared__ KeyT s_red_k[2][kSWarps];
-    __shared__ int s_flag[2];
-    __shared__ int s_star[3];            // straddling bin: index, base, count
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_genes = a.n_genes, cutoff = a.rank_cutoff;
-
-    for (int i = tid; i < 2 * a.tab.n_acc; i += kS) acc_lo[i] = 0u;
-    __syncthreads();
-
-    for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
-        RowView<ValT> row;
-        if (IN == IN_CSR) {
-            const int64_t begin = a.indptr[cell];
-            row.vals = a.data + begin;
-            row.cols = a.indices + begin;
-            row.count = (int)(a.indptr[cell + 1] - begin);
-        } else {
-            row.vals = a.dense + cell * a.row_stride;
-            row.cols = nullptr;
-            row.count = n_genes;
-        }
-        bool general = false;
-        int why = 1;
-
-        // ---------------- PASS A: statistics --------------------------------------------------------------------
-        int c_exp = 0, c_pos = 0;
-        KeyT kmin = KT::KEY_ZERO, kmax = 0;
-        stream_row<kS>(row, [&](bool ex, KeyT kk, int) {
-            if (ex) {
-                ++c_exp;
-                if (kk < KT::KEY_ZERO) { ++c_pos; kmin = tmin(kmin, kk); kmax = tmax(kmax, kk); }
-            }
-        });
-        c_exp = warp_sum(c_exp);
-        c_pos = warp_sum(c_pos);
-        kmin = warp_min(kmin);
-        kmax = warp_max(kmax);
-        if (lane == 0) {
-            s_red_i[0][warp] = c_exp; s_red_i[1][warp] = c_pos;
-            s_red_k[0][warp] = kmin; s_red_k[1][warp] = kmax;
-        }
-        for (int b = tid; b <= kNb1; b += kS) h1[b] = 0u;
-        if (tid < (kNb1 >> 5)) mixed[tid] = 0u;
-        if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; s_cnt[1] = 0; s_star[0] = -1; s_star[1] = 0; s_star[2] = 0; }
-        __syncthreads();
-        int m, n_gt;
-        {
-            const bool has = lane < kSWarps;
-            m = warp_sum(has ? s_red_i[0][lane] : 0);
-            n_gt = warp_sum(has ? s_red_i[1][lane] : 0);
-            kmin = warp_min(has ? s_red_k[0][lane] : (KeyT)KT::KEY_ZERO);
-            kmax = warp_max(has ? s_red_k[1][lane] : (KeyT)0);
-        }
-        const int n_zero = n_genes - m;
-        if (cutoff - n_gt - n_zero > 0) { general = true; why = 2; }
-
-        if (!general && n_gt > 0) {
-            const KeyT range = kmax - kmin;
-            int nbits = 0;
-            if (range) nbits = (sizeof(KeyT) == 8) ? 64 - __clzll((long long)range) : 32 - __clz((int)range);
-            const int shift = max(0, nbits - kNb1Log);
-            // ---------------- PASS B: level-1 histogram + representative key per bin --------------------------
-            stream_row<kS>(row, [&](bool ex, KeyT kk, int) {
-                if (ex && kk < KT::KEY_ZERO) {
-                    const uint32_t b = (uint32_t)((kk - kmin) >> shift);
-                    atomicAdd(&h1[b], 1u);
-                    rep[b] = kk;
-                }
-            });
-            __syncthreads();
-            {   // exclusive scan of the bin counts; find the bin that straddles the cutoff
-                constexpr int per = kNb1 / kS;
-                const int b0 = tid * per;
-                int cnt[per];
-                int local = 0;
-#pragma unroll
-                for (int j = 0; j < per; ++j) { cnt[j] = (int)h1[b0 + j]; local += cnt[j]; }
-                int total;
-                int run = block_excl_scan_n<kS, false>(local, s_scan, total);
-#pragma unroll
-                for (int j = 0; j < per; ++j) {
-                    h1[b0 + j] = (uint32_t)run;
-                    if (run < cutoff && run + cnt[j] >= cutoff) { s_star[0] = b0 + j; s_star[1] = run; s_star[2] = cnt[j]; }
-                    run += cnt[j];
-                }
-                if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
-            }
-            __syncthreads();
-            const int star = s_star[0];                       // -1: every positive ranks below the cutoff
-            const int star_base = s_star[1], star_cnt = s_star[2];
-            const int q = cutoff - star_base;                 // entries wanted from the straddling bin
-            const bool prune = star >= 0 && star_cnt > 64;
-            int s_lim = star_cnt;                             // kept position sub-buckets of the straddling bin
-            if (prune) s_lim = min(star_cnt, q + 8 * ((int)sqrtf((float)q) + 1) + 32);
-            const int n_s = (star >= 0 ? star_base + s_lim : n_gt);   // sub-bucket id space
-            if (n_s > kCapS) {
-                general = true;
-            } else {
-                // ---------------- PASS C: selection into the staging arrays --------------------------------------
-                stream_row<kS>(row, [&](bool ex, KeyT kk, int col) {
-                    bool keep = false;
-                    PosT ps = 0;
-                    if (ex && kk < KT::KEY_ZERO) {
-                        const uint32_t b = (uint32_t)((kk - kmin) >> shift);
-                        if ((int)h1[b] < cutoff) {
-                            keep = true;
-                            ps = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
-                            const bool differs = rep[b] != kk;
-                            if ((int)b == star && prune) {
-                                if (differs) s_flag[1] = 1;        // a big straddling bin must hold one key
-                                const uint32_t sub = (uint32_t)(((unsigned long long)((unsigned)ps) * (unsigned)star_cnt * a.inv_ng) >> 32);
-                                keep = (int)min(sub, (uint32_t)star_cnt - 1u) < s_lim;
-                            } else if (differs) {
-                                atomicOr(&mixed[b >> 5], 1u << (b & 31));
-                            }
-                        }
-                    }
-                    const unsigned mk = __ballot_sync(0xffffffffu, keep);
-                    if (mk) {
-                        int wbase = 0;
-                        const int leader = __ffs(mk) - 1;
-                        if (lane == leader) wbase = atomicAdd(&s_cnt[1], __popc(mk));
-                        wbase = __shfl_sync(0xffffffffu, wbase, leader);
-                        if (keep) {
-                            const int idx = wbase + __popc(mk & lanemask_lt());
-                            if (idx < kCapS) { fk[idx] = kk; fp[idx] = ps; }
-                        }
-                    }
-                });
-                __syncthreads();
-                const int n_kept = s_cnt[1];
-                // exactness of the pruning: the kept slice of the straddling bin must hold at least q entries
-                if (n_kept > kCapS || s_flag[1] || (prune && n_kept - star_base < q)) {
-                    general = true;
-                    why = s_flag[1] ? 3 : 1;
-                }
-                KeyT key[kSItems];
-                PosT pos[kSItems];
-                const int nk = general ? 0 : (n_kept + kS - 1) / kS;
-#pragma unroll
-                for (int k = 0; k < kSItems; ++k) {
-                    const int i = k * kS + tid;
-                    key[k] = (k < nk && i < n_kept) ? fk[i] : KT::KEY_ZERO;
-                    pos[k] = (k < nk && i < n_kept) ? fp[i] : (PosT)0;
-                }
-                __syncthreads();              // staging and rep are free again
-                if (!general) {
-                    // S3: clear level-2 histogram
-                    for (int b = tid; b <= n_s; b += kS) h2[b] = 0u;
-                    __syncthreads();
-                    // S4: level-2 histogram
-                    uint32_t sbs[kSItems];
-#pragma unroll
-                    for (int k = 0; k < kSItems; ++k) {
-                        sbs[k] = 0xFFFFFFFFu;
-                        if (k < nk && key[k] < KT::KEY_ZERO) {
-                            const uint32_t bin = (uint32_t)((key[k] - kmin) >> shift);
-                            const uint32_t base = h1[bin];
-                            const uint32_t c = h1[bin + 1] - base;
-                            uint32_t sub = 0;
-                            if (!((mixed[bin >> 5] >> (bin & 31)) & 1u)) {
-                                sub = (uint32_t)(((unsigned long long)((unsigned)pos[k]) * c * a.inv_ng) >> 32);
-                                sub = min(sub, c - 1u);
-                            }
-                            const uint32_t sb = base + sub;
-                            const uint32_t got = atomicAdd(&h2[sb], 1u);
-                            if (got >= (uint32_t)kMaxSub) s_flag[0] = 1;
-                            sbs[k] = (sb << 8) | min(got, 255u);
-                        }
-                    }
-                    __syncthreads();
-                    if (s_flag[0]) {
-                        general = true;
-                        why = 3;
-                    } else {
-                        // S5: exclusive scan of level-2 counts
-                        {
-                            const int per = (n_s + kS - 1) / kS;
-                            const int b0 = tid * per, b1 = min(b0 + per, n_s);
-                            int local = 0;
-                            for (int b = b0; b < b1; ++b) local += (int)h2[b];
-                            int total;
-                            int run = block_excl_scan_n<kS, false>(local, s_scan2, total);
-                            for (int b = b0; b < b1; ++b) {
-                                const int c = (int)h2[b];
-                                h2[b] = (uint32_t)run;
-                                run += c;
-                            }
-                            if (tid == 0) h2[n_s] = (uint32_t)n_kept;
-                        }
-                        __syncthreads();
-                        // S6: entries into sub-bucket order (sub-buckets starting at or beyond the cutoff are dropped)
-#pragma unroll
-                        for (int k = 0; k < kSItems; ++k) {
-                            if (k < nk && sbs[k] != 0xFFFFFFFFu) {
-                                const uint32_t b2 = h2[sbs[k] >> 8];
-                                if ((int)b2 < cutoff) store.put(b2 + (sbs[k] & 255u), key[k], pos[k]);
-                                else sbs[k] = 0xFFFFFFFFu;
-                            }
-                        }
-                        __syncthreads();
-                        // S7: exact rank inside the sub-bucket
-                        uint32_t mv[kSItems], tb[kSItems], tc[kSItems];
-#pragma unroll
-                        for (int k = 0; k < kSItems; ++k) {
-                            mv[k] = 0u; tb[k] = 0u; tc[k] = 0u;
-                            if (k < nk && sbs[k] != 0xFFFFFFFFu) {
-                                const uint32_t sb = sbs[k] >> 8;
-                                const uint32_t b = h2[sb], e = h2[sb + 1];
-                                const unsigned long long mine = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)pos[k];
-                                uint32_t rank = b;
-                                for (uint32_t j = b; j < e; ++j) rank += store.before(j, key[k], pos[k], mine);
-                                if ((int)rank < cutoff) {
-                                    mv[k] = (uint32_t)(cutoff - (int)rank);
-                                    tb[k] = __ldg(a.tab.tptr + (unsigned)pos[k]);
-                                    tc[k] = __ldg(a.tab.tptr + (unsigned)pos[k] + 1) - tb[k];
-                                }
-                            }
-                        }
-                        __syncthreads();
-                        // S8: scatter through the per-warp queue, two rounds of kSItems/2 slots (a warp owns
-                        //     ~180 genes below the cutoff, i.e. ~340 table entries: more than one queue holds)
-                        {
-                            uint32_t* const qj = h2 + warp * kQS;
-                            PosT* const qm = fp + warp * kQS;
-#pragma unroll
-                            for (int half = 0; half < 2; ++half) {
-                                constexpr int H = kSItems / 2;
-                                int mine_n = 0;
-#pragma unroll
-                                for (int k = 0; k < H; ++k) mine_n += (int)tc[half * H + k];
-                                int incl = mine_n;
-#pragma unroll
-                                for (int o = 1; o < 32; o <<= 1) {
-                                    const int tt = __shfl_up_sync(0xffffffffu, incl, o);
-                                    if (lane >= o) incl += tt;
-                                }
-                                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                                if (total == 0) continue;
-                                if (total <= kQS) {
-                                    int at = incl - mine_n;
-#pragma unroll
-                                    for (int k = 0; k < H; ++k) {
-                                        for (uint32_t i = 0; i < tc[half * H + k]; ++i) {
-                                            qj[at] = tb[half * H + k] + i;
-                                            qm[at] = (PosT)mv[half * H + k];
-                                            ++at;
-                                        }
-                                    }
-                                    flush_queue<ACC64, PosT>(a.tab, acc_lo, acc_hi, qj, qm, total);
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < H; ++k)
-                                        for (uint32_t i = 0; i < tc[half * H + k]; ++i)
-                                            apply_entry<ACC64>(a.tab, acc_lo, acc_hi, tb[half * H + k] + i, mv[half * H + k]);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (!general && n_gt < cutoff) {
-            // ---------------- ZEROS ---------------------------------------------------------------------------------
-            const int q_zero = cutoff - n_gt;
-            if (a.stats != nullptr && tid == 0) atomicAdd(a.stats + 4, 1ull);
-            for (int w = tid; w < a.n_words; w += kS) s_bits[w] = 0u;
-            __syncthreads();
-            stream_row<kS>(row, [&](bool ex, KeyT, int col) {
-                if (ex) {
-                    const unsigned p = (unsigned)__ldg(static_cast<const PosT*>(a.inv_perm) + col);
-                    atomicOr(&s_bits[p >> 5], 1u << (p & 31));
-                }
-            });
-            __syncthreads();
-            const int per = (a.n_words + kS - 1) / kS;
-            const int w0 = tid * per, w1 = min(w0 + per, a.n_words);
-            int local = 0;
-            for (int w = w0; w < w1; ++w) local += __popc(s_bits[w]);
-            int total;
-            int run = block_excl_scan_n<kS>(local, s_scan, total);
-            for (int w = w0; w < w1; ++w) {
-                s_wpre[w] = (uint32_t)run;
-                run += __popc(s_bits[w]);
-            }
-            __syncthreads();
-            for (int p = tid; p < n_genes; p += kS) {
-                const int w = p >> 5;
-                const uint32_t bw = s_bits[w];
-                const int z0 = (w << 5) - (int)s_wpre[w];
-                if (z0 >= q_zero) break;
-                if (!((bw >> (p & 31)) & 1u)) {
-                    const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                    if (z < q_zero) scatter_packed<ACC64>(a.tab, acc_lo, acc_hi, (unsigned)p, (unsigned)(q_zero - z));
-                }
-            }
-        }
-        if (!general && a.out_nnz != nullptr && tid == 0) a.out_nnz[cell] = m;
-        if (a.stats != nullptr && tid == 0) {
-            atomicAdd(a.stats + 0, 1ull);
-            if (general) atomicAdd(a.stats + why, 1ull);
-        }
-        if (general) {
-            __syncthreads();
-            general_cell<ValT, PosT, IN, ACC64, kS>(a, cell, s_bits, s_wpre, acc_lo, acc_hi, s_cnt, s_scan, smem);
-        }
-        __syncthreads();
-        write_aucs_packed<ACC64, kS>(a.tab, acc_lo, acc_hi, a.out_auc + cell * (int64_t)a.tab.n_regulons);
-        __syncthreads();
-    }
-}
-
-#endif  // AUCELL_B200_WITH_STREAMING
 
 // aucell4r path: AUCs from an existing ranking matrix (reference aucell.py:98-182; ctxcore auc2d): the same
 // scatter, driven straight from the ranking row (T is indexed by the ranking matrix' own columns).

@@ -155,52 +155,20 @@ int resident_ctas(K kernel, int threads, int smem) {
     return n;
 }
 
-// Which fused kernel.  aucell_fused_kernel (512 threads, entries resident in registers) is the default: measured
-// 17.6 M cells/s on the cfg4 shape against 15.0 M cells/s for the streaming 256-thread variant
-// (aucell_fused_sel_kernel: three passes over the row + exact position pruning; fewer instructions per cell but more
-// L2 round trips, 45 % vs 57 % issue-slot utilisation).  AUCELL_B200_FUSED=streaming selects the variant for A/B runs
-// when its register capacity fits the cutoff.
-inline bool use_streaming_kernel(const aucell_plan* p) {
-#ifndef AUCELL_B200_WITH_STREAMING
-    (void)p;
-    return false;
-#else
-    const char* env = getenv("AUCELL_B200_FUSED");
-    if (!env || strcmp(env, "streaming") != 0) return false;
-    const double c = (double)p->rank_cutoff;
-    return c + 8.0 * (std::sqrt(c) + 1.0) + 96.0 <= (double)kCapS;
-#endif
-}
-
 template <typename ValT, typename PosT, int IN>
-int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st,
-                 int key_bytes, bool streaming) {
+int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_cells, cudaStream_t st, int key_bytes) {
     int grid = 0;
-#ifdef AUCELL_B200_WITH_STREAMING
-    const int threads = streaming ? kS : kF;
-    const int cap_unused = 0; (void)cap_unused;
-#else
-    const int threads = kF;
-#endif
 #define LAUNCH_FUSED(KERNEL)                                                                              \
     do {                                                                                                  \
         auto k = KERNEL;                                                                                  \
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
-        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, threads, smem));   \
+        grid = (int)std::min<int64_t>(n_cells, (int64_t)p->sm_count * resident_ctas(k, kF, smem));        \
         int rc = get_scratch(p, st, key_bytes, grid, a.scratch_cap, &a.scratch_key, &a.scratch_pos);      \
         if (rc) return rc;                                                                                \
-        k<<<grid, threads, smem, st>>>(a);                                                                \
+        k<<<grid, kF, smem, st>>>(a);                                                                     \
     } while (0)
-#ifdef AUCELL_B200_WITH_STREAMING
-    if (streaming) {
-        if (p->acc64) LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, true>));
-        else LAUNCH_FUSED((aucell_fused_sel_kernel<ValT, PosT, IN, false>));
-    } else
-#endif
-    {
-        if (p->acc64) LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, true>));
-        else LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, false>));
-    }
+    if (p->acc64) LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, true>));
+    else LAUNCH_FUSED((aucell_fused_kernel<ValT, PosT, IN, false>));
 #undef LAUNCH_FUSED
     launch_counter().fetch_add(1);
     CK(cudaGetLastError());
@@ -225,33 +193,16 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     cudaStream_t st = (cudaStream_t)stream;
     const int key_bytes = (int)sizeof(typename KeyOf<ValT>::type);
     const int pos_bytes = p->pos16 ? 2 : 4;
-    const bool streaming = use_streaming_kernel(p);
-#ifdef AUCELL_B200_WITH_STREAMING
-    const int cap = streaming ? kCapS : kCapF;
-#else
-    const int cap = kCapF;
-#endif
 
     FusedArgs<ValT> a;
     memset(&a, 0, sizeof a);
-    int off = 0;
-    if (!streaming) {
-        // aucell_fused_kernel: compile-time offsets up to the accumulators (fused_offsets), then bitmap + prefixes
-        const FusedOffsets L = fused_offsets(key_bytes, pos_bytes);
-        a.off_h1 = L.h1; a.off_h2 = L.h2; a.off_fk = L.fk; a.off_fp = L.fp; a.off_mixed = L.mixed;
-        a.off_acc = L.acc; off = align16(L.acc + p->n_acc * 8);
-        a.off_bits = off; off = align16(off + p->n_words * 4);
-        a.off_wpre = off; off = align16(off + p->n_words * 4);
-    } else {
-        a.off_h1 = off; off = align16(off + (kNb1 + 1) * 4);
-        a.off_h2 = off; off = align16(off + std::max((cap + 1) * 4, kNb1 * key_bytes));   // also holds one key per bin
-        a.off_fk = off; off = align16(off + cap * (key_bytes == 4 ? 8 : key_bytes));   // packed (key, pos) for 32-bit keys
-        a.off_fp = off; off = align16(off + cap * pos_bytes);
-        a.off_mixed = off; off = align16(off + kNb1 / 8);
-        a.off_bits = off; off = align16(off + p->n_words * 4);
-        a.off_wpre = off; off = align16(off + p->n_words * 4);
-        a.off_acc = off; off = align16(off + p->n_acc * 8);
-    }
+    // compile-time offsets up to the accumulators (fused_offsets), then the zero-fill bitmap + its prefixes
+    const FusedOffsets L = fused_offsets(key_bytes, pos_bytes);
+    a.off_h1 = L.h1; a.off_h2 = L.h2; a.off_fk = L.fk; a.off_fp = L.fp; a.off_mixed = L.mixed;
+    a.off_acc = L.acc;
+    int off = align16(L.acc + p->n_acc * 8);
+    a.off_bits = off; off = align16(off + p->n_words * 4);
+    a.off_wpre = off; off = align16(off + p->n_words * 4);
     {
         int g = 2;
         while ((int64_t)g * 2 * (key_bytes + pos_bytes) <= a.off_mixed - a.off_h1) g <<= 1;
@@ -272,10 +223,10 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
     if constexpr (IN == IN_CSR16) {       // 16-bit indices imply 16-bit positions: one instantiation
-        return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, false);
+        return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
     } else {
-        if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
-        return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes, streaming);
+        if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
+        return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes);
     }
 }
 

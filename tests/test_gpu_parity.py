@@ -269,8 +269,7 @@ def test_fused_dense_and_csr_vs_oracle_edge_cells(unweighted, fused_variant):
 
 @pytest.fixture(params=["default"])
 def fused_variant(request):
-    """Hook for A/B builds (-DAUCELL_B200_WITH_STREAMING + AUCELL_B200_FUSED=streaming); the default build has one
-    fused kernel."""
+    """Hook for A/B builds of kernel variants; the tree holds one fused kernel."""
     return request.param
 
 
