@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTED_SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.aucell_b200_abi_version() == 1
+    assert lib.aucell_b200_abi_version() == 2
     assert lib.aucell_b200_launch_count() >= 0
 
 
