@@ -6,7 +6,13 @@ import numpy as np, torch
 import synth
 from pyscenic_b200.plan import AUCellPlan, derive_rank_cutoff
 
+import os
+ONLY = os.environ.get("ONLY", "")
+
+
 def run(name, n_cells, n_genes, mean_nnz, R=500, f64=False, sigma=0.35, thr=0.05):
+    if ONLY and ONLY not in name:
+        return
     rs = np.random.RandomState(1)
     reg = synth.make_regulons(rs, n_genes, R, 10, 400, weighted=True)
     cutoff = derive_rank_cutoff(thr, n_genes)
@@ -31,3 +37,4 @@ run("cfg4 shape, float64 values", 100000, 27998, 1960, f64=True)
 run("long rows: 8,400 stored entries per cell (30 % of 27,998)", 40000, 27998, 8400)
 run("very sparse cells: 60 stored entries per cell", 400000, 27998, 60)
 run("70,001 genes (32-bit positions), 3,500 entries per cell", 60000, 70001, 3500)
+run("deep cells: 6,000 entries per cell of 60,000 genes (selection pruned by position)", 40000, 60000, 6000)

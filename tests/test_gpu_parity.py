@@ -463,6 +463,39 @@ def test_config3_full_size_properties_and_spot_check():
     assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))
 
 
+@pytest.mark.parametrize("n_genes", [60000, 70001])
+def test_deep_cells_whose_selection_exceeds_the_register_capacity(n_genes):
+    """Cells with more stored entries than the register capacity (4,096) whose tie class at the cutoff is so large
+    that even the selection exceeds it (they take the general sort today; pruning the straddling class by shuffled
+    position is the planned fix), 16- and 32-bit positions.  One row's straddling bin holds two adjacent keys."""
+    import torch
+
+    n_cells = 48
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 6000, seed=41, device="cuda", sigma=0.25)
+    ip = indptr.cpu().numpy()
+    assert (np.diff(ip) > 4500).sum() >= n_cells // 2 and np.diff(ip)[3] > 4500
+    dv = data.cpu().numpy().copy()
+    # cell 3: the lowest class gets a second, adjacent value -> the straddling bin holds two keys
+    s3, e3 = ip[3], ip[4]
+    lo = dv[s3:e3].min()
+    sel = np.flatnonzero(dv[s3:e3] == lo)[::2]
+    dv[s3 + sel] = np.nextafter(np.float32(lo), np.float32(10.0))
+    data = torch.from_numpy(dv).cuda()
+    rs = np.random.RandomState(6)
+    reg = synth.make_regulons(rs, n_genes, 80, 10, 400, weighted=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(42).permutation(n_genes)
+    X = synth.csr_to_dense(ip, indices.cpu().numpy(), dv, n_genes)
+    want = oracle_auc(X, perm, reg, cutoff)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_csr(indptr, indices, data).cpu().numpy()
+        stats = plan.path_stats()
+        got_d = plan.aucell_dense(torch.from_numpy(X).cuda()).cpu().numpy()
+    assert_auc_close(got, want)
+    assert np.array_equal(got, got_d)
+    assert stats["cells"] == n_cells
+
+
 @pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.6, False), (0.6, True)])
 def test_from_rankings_hit_list_and_its_overflow(thr, unweighted):
     """aucell4r kernel: ranks below the cutoff are collected into a 4,096-entry list before they are scattered; with
