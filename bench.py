@@ -22,7 +22,6 @@ the reference itself cannot run -- ctxcore is not installed) on a bounded cell s
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

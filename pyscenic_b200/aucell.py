@@ -31,7 +31,7 @@ import numpy as np
 import pandas as pd
 
 from . import _native
-from .plan import AUCellPlan, RegulonTables, derive_rank_cutoff, permutation_from_seed, prepare_regulons
+from .plan import AUCellPlan, permutation_from_seed, prepare_regulons
 
 LOGGER = logging.getLogger(__name__)
 # The reference stores rankings as unsigned 32 bit integers (aucell.py:19-22).

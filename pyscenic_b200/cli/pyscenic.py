@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import argparse
 import logging
-import os
 import sys
 from multiprocessing import cpu_count
 from pathlib import PurePath

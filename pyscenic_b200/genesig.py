@@ -18,7 +18,7 @@ from collections.abc import Iterable, Mapping
 from itertools import repeat
 from operator import itemgetter
 from types import MappingProxyType
-from typing import Dict, FrozenSet, List, Optional, Tuple
+from typing import FrozenSet, List, Tuple
 
 __all__ = ["GeneSignature", "Regulon", "openfile"]
 

@@ -9,7 +9,7 @@ the ranking is dominated by ties -- like real scRNA-seq data, and the hard case 
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple
+from typing import Optional
 
 import numpy as np
 
