@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 2   /* 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -153,6 +153,17 @@ int aucell_plan_last_host_bytes(const aucell_plan_t* plan, int64_t* out2);
  * the device): out5 = { cells, general path: more than 4096 explicit entries, general path: negative values ranked
  * below the cutoff, general path: crowded value bin, cells that needed zeros below the cutoff }. */
 int aucell_plan_path_stats(const aucell_plan_t* plan, uint64_t* out5, int reset);
+/* The CSR entry points with float32 values run two kernels: aucell_tie_kernel ranks every cell whose values fall into
+ * a few tie classes (count data), and hands the rest (rows of more than 4096 stored entries, negative / NaN values,
+ * continuous values) to aucell_fused_kernel through a to-do list.  Both add the same integers, so the output does not
+ * depend on which kernel ranked a cell.  enable = 0 sends every cell to the general kernel, for testing; returns whether
+ * the plan qualifies for the tie-class kernel at all (16-bit positions, non-negative weights of bounded range) through
+ * *out_available (nullable). */
+int aucell_plan_set_fast_path(aucell_plan_t* plan, int enable, int* out_available);
+/* Cells per outcome of aucell_tie_kernel since the last reset (synchronises the device): out8 = { ranked there, handed
+ * over: more stored entries than a cell group holds, negative / NaN value, duplicate or out-of-range column, two values
+ * in one class bin, more than 256 tail entries, skipped (the group saw mostly unsuitable cells), reserved }. */
+int aucell_plan_fast_stats(const aucell_plan_t* plan, uint64_t* out8, int reset);
 /* number of kernels this library has launched on the calling process since load (bench.py gpu_launches) */
 int64_t aucell_b200_launch_count(void);
 

@@ -59,6 +59,8 @@ EXPORTED_SYMBOLS = [
     "aucell_plan_path_stats",
     "aucell_plan_last_host_bytes",
     "aucell_rss_f64",
+    "aucell_plan_set_fast_path",
+    "aucell_plan_fast_stats",
 ]
 
 
@@ -201,6 +203,10 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_plan_path_stats.restype = c_int
         lib.aucell_plan_last_host_bytes.argtypes = [p, p]
         lib.aucell_plan_last_host_bytes.restype = c_int
+        lib.aucell_plan_set_fast_path.argtypes = [p, c_int, p]
+        lib.aucell_plan_set_fast_path.restype = c_int
+        lib.aucell_plan_fast_stats.argtypes = [p, p, c_int]
+        lib.aucell_plan_fast_stats.restype = c_int
         lib.aucell_rss_f64.argtypes = [c_int, p, i64, i64, i32, p, i32, p, p, p]
         lib.aucell_rss_f64.restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]

@@ -145,87 +145,132 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
     PCK(cudaMalloc(&p->d_inv_perm, sizeof(int32_t) * n_genes));
     PCK(cudaMemcpy(p->d_inv_perm, inv.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice));
     if (p->pos16) {
-        std::vector<uint16_t> inv16((size_t)n_genes);
+        const size_t n16 = ((size_t)n_genes + 7) & ~(size_t)7;      // aucell_tie_kernel copies it in 128-bit vectors
+        std::vector<uint16_t> inv16(n16, 0);
         for (int64_t g = 0; g < n_genes; ++g) inv16[g] = (uint16_t)inv[g];
-        PCK(cudaMalloc(&p->d_inv_perm16, sizeof(uint16_t) * n_genes));
-        PCK(cudaMemcpy(p->d_inv_perm16, inv16.data(), sizeof(uint16_t) * n_genes, cudaMemcpyHostToDevice));
+        PCK(cudaMalloc(&p->d_inv_perm16, sizeof(uint16_t) * n16));
+        PCK(cudaMemcpy(p->d_inv_perm16, inv16.data(), sizeof(uint16_t) * n16, cudaMemcpyHostToDevice));
     }
 
     if (n_regulons > 0) {
         const int64_t nnz = h_reg_indptr[n_regulons];
         p->reg_nnz = nnz;
         p->acc64 = p->weighted || rank_cutoff > 65535;
-        // ---- accumulators and fixed-point weights (see fused_kernel.cuh, SCATTER) ------------------------
-        std::vector<int32_t> acc_first((size_t)n_regulons, -1);
-        std::vector<uint8_t> acc_parts((size_t)n_regulons, 0);
+        // ---- accumulators and fixed-point weights (see fused_kernel.cuh SCATTER, tie_kernel.cuh P6) ------------
+        // Two quantisations.  "tie": what aucell_tie_kernel can accumulate in pairs of u32 limbs -- non-negative
+        // weights, W < 2^Bt per part, at most two parts per regulon, the smallest weight keeping >= 22 significant bits
+        // (relative error <= 2.4e-7 on every single term; the sum of non-negative terms inherits it).  Both kernels
+        // then add the SAME integers, so a cell gets the same bits whichever kernel ranks it.  "wide": 48-bit signed
+        // weights, up to four parts, >= 24 bits (aucell_fused_kernel only) for everything else.
+        std::vector<int32_t> acc_first;
+        std::vector<uint8_t> acc_parts;
         std::vector<double> acc_scale;
         struct TEnt { int32_t pos; uint32_t acc; long long w; };
         std::vector<TEnt> ents;
-        ents.reserve((size_t)nnz + 16);
-        for (int r = 0; r < n_regulons; ++r) {
-            const int64_t b = h_reg_indptr[r], e = h_reg_indptr[r + 1];
-            for (int64_t k = b; k < e; ++k) {
-                if (h_reg_cols[k] < 0 || h_reg_cols[k] >= n_genes) {
-                    aucell_plan_destroy(p);
-                    return fail(AUCELL_ERR_INVALID, "regulon gene column out of range");
+        int Bt = 0, tieL = 0;
+        bool tie_q = p->pos16 && rank_cutoff >= 1 && rank_cutoff <= 65535 && n_genes >= 1;
+        {
+            const char* env = getenv("AUCELL_B200_TIE");
+            if (env && env[0] == '0') tie_q = false;
+        }
+        if (tie_q && p->weighted) {
+            int64_t max_hits = 1;
+            for (int r = 0; r < n_regulons; ++r)
+                if (h_reg_valid[r])
+                    max_hits = std::max<int64_t>(max_hits, h_reg_indptr[r + 1] - h_reg_indptr[r]);   // (a gene listed twice counts twice)
+            int nrb = 0;
+            while (((int64_t)1 << nrb) < max_hits) ++nrb;          // hits <= 2^nrb
+            int c = 0;
+            while (((int64_t)1 << c) <= rank_cutoff) ++c;          // multipliers cutoff - rank < 2^c
+            tieL = 32 - nrb;                                       // sum of hits low limbs (< 2^L each) fits 32 bits
+            Bt = std::min(31, 63 - c - 2 * nrb);                   // ... and so does the sum of the high limbs
+            if (Bt < 24 || tieL < 1 || tieL > 31) tie_q = false;
+            for (int64_t k = 0; tie_q && k < nnz; ++k)
+                if (!(h_reg_weights[k] >= 0.0) || !std::isfinite(h_reg_weights[k])) tie_q = false;
+        }
+        auto quantise = [&](bool tie) -> int {
+            acc_first.assign((size_t)n_regulons, -1);
+            acc_parts.assign((size_t)n_regulons, 0);
+            acc_scale.clear();
+            ents.clear();
+            ents.reserve((size_t)nnz + 16);
+            for (int r = 0; r < n_regulons; ++r) {
+                const int64_t b = h_reg_indptr[r], e = h_reg_indptr[r + 1];
+                for (int64_t k = b; k < e; ++k)
+                    if (h_reg_cols[k] < 0 || h_reg_cols[k] >= n_genes)
+                        return fail(AUCELL_ERR_INVALID, "regulon gene column out of range");
+                if (!h_reg_valid[r]) continue;
+                if (!(h_reg_max_auc[r] > 0.0) || e == b)
+                    return fail(AUCELL_ERR_INVALID, "valid regulons need max_auc > 0 and at least one gene");
+                const int first = (int)acc_scale.size();
+                acc_first[r] = first;
+                if (!p->weighted) {
+                    acc_parts[r] = 1;
+                    acc_scale.push_back(1.0);
+                    for (int64_t k = b; k < e; ++k) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first, 1ll});
+                    continue;
+                }
+                double wmax = 0.0, wmin = 0.0;
+                for (int64_t k = b; k < e; ++k) {
+                    const double aw = std::fabs(h_reg_weights[k]);
+                    if (!std::isfinite(aw)) return fail(AUCELL_ERR_INVALID, "regulon weights must be finite");
+                    if (aw > 0.0) {
+                        wmax = std::max(wmax, aw);
+                        wmin = (wmin == 0.0) ? aw : std::min(wmin, aw);
+                    }
+                }
+                if (wmax == 0.0) {  // all-zero weights cannot give max_auc > 0, but stay safe
+                    acc_parts[r] = 1;
+                    acc_scale.push_back(1.0);
+                    continue;
+                }
+                int B, max_parts;
+                double need;                           // the smallest weight, scaled, must reach this
+                if (tie) {
+                    B = Bt; max_parts = 2; need = 2097152.0;            // 2^21: 22 significant bits
+                } else {
+                    // W = llrint(w * 2^s): |sum| <= hits * Wmax * cutoff must stay below 2^62
+                    const double hits = (double)std::min<int64_t>(e - b, std::max<int64_t>(rank_cutoff, 1));
+                    B = 62 - (int)std::ceil(std::log2(hits * (double)std::max<int64_t>(rank_cutoff, 1)));
+                    B = std::max(24, std::min(B, 46));   // W is stored in 48 signed bits
+                    max_parts = 4; need = 8388608.0;                    // 2^23: 24 significant bits
+                }
+                int ex = 0;
+                std::frexp(wmax, &ex);                 // wmax = f * 2^ex, f in [0.5, 1)
+                const int s1 = B - ex;                 // wmax * 2^s1 in [2^(B-1), 2^B)
+                // parts: W_k = round(residual_{k-1} * 2^(s1 + (k-1)(B-1))), enough of them for the smallest weight
+                int parts = 1;
+                while (parts < max_parts && std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < need) ++parts;
+                if (std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < need) {
+                    if (tie) return 1;                 // not representable here: the caller falls back to "wide"
+                    return fail(AUCELL_ERR_UNSUPPORTED,
+                                "the weights of one regulon span more than ~45 orders of magnitude; cannot guarantee 1e-6");
+                }
+                acc_parts[r] = (uint8_t)parts;
+                for (int k = 0; k < parts; ++k) acc_scale.push_back(std::ldexp(1.0, -(s1 + k * (B - 1))));
+                for (int64_t k = b; k < e; ++k) {
+                    double res = h_reg_weights[k];
+                    for (int l = 0; l < parts; ++l) {
+                        const int sl = s1 + l * (B - 1);
+                        // unsigned limbs cannot take a negative residual: every part but the last rounds down
+                        const long long Wl = (tie && l + 1 < parts) ? (long long)std::floor(std::ldexp(res, sl))
+                                                                    : std::llrint(std::ldexp(res, sl));
+                        if (Wl != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)(first + l), Wl});
+                        res -= std::ldexp((double)Wl, -sl);    // exact: Wl * 2^-sl is res on a coarser grid
+                    }
                 }
             }
-            if (!h_reg_valid[r]) continue;
-            if (!(h_reg_max_auc[r] > 0.0) || e == b) {
+            return AUCELL_OK;
+        };
+        {
+            int qrc = tie_q ? quantise(true) : 1;
+            if (qrc == 1) {
+                if (p->weighted) tie_q = false;        // (unit weights never return 1)
+                qrc = quantise(false);
+            }
+            if (qrc != AUCELL_OK) {
                 aucell_plan_destroy(p);
-                return fail(AUCELL_ERR_INVALID, "valid regulons need max_auc > 0 and at least one gene");
-            }
-            const int first = (int)acc_scale.size();
-            acc_first[r] = first;
-            if (!p->weighted) {
-                acc_parts[r] = 1;
-                acc_scale.push_back(1.0);
-                for (int64_t k = b; k < e; ++k) ents.push_back({inv[h_reg_cols[k]], (uint32_t)first, 1ll});
-                continue;
-            }
-            // W = llrint(w * 2^s): |sum| <= hits * Wmax * cutoff must stay below 2^62
-            double wmax = 0.0, wmin = 0.0;
-            for (int64_t k = b; k < e; ++k) {
-                const double aw = std::fabs(h_reg_weights[k]);
-                if (!std::isfinite(aw)) {
-                    aucell_plan_destroy(p);
-                    return fail(AUCELL_ERR_INVALID, "regulon weights must be finite");
-                }
-                if (aw > 0.0) {
-                    wmax = std::max(wmax, aw);
-                    wmin = (wmin == 0.0) ? aw : std::min(wmin, aw);
-                }
-            }
-            if (wmax == 0.0) {  // all-zero weights cannot give max_auc > 0, but stay safe
-                acc_parts[r] = 1;
-                acc_scale.push_back(1.0);
-                continue;
-            }
-            const double hits = (double)std::min<int64_t>(e - b, std::max<int64_t>(rank_cutoff, 1));
-            int B = 62 - (int)std::ceil(std::log2(hits * (double)std::max<int64_t>(rank_cutoff, 1)));
-            B = std::max(24, std::min(B, 46));   // W is stored in 48 signed bits
-            int ex = 0;
-            std::frexp(wmax, &ex);                 // wmax = f * 2^ex, f in [0.5, 1)
-            const int s1 = B - ex;                 // wmax * 2^s1 in [2^(B-1), 2^B)
-            // limbs: W_k = llrint(residual_{k-1} * 2^(s1 + (k-1)(B-1))).  Enough limbs that the smallest weight keeps
-            // at least 24 significant bits (relative error <= 6e-8 on every single term).
-            int parts = 1;
-            while (parts < 4 && std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < 8388608.0) ++parts;
-            if (std::ldexp(wmin, s1 + (parts - 1) * (B - 1)) < 8388608.0) {
-                aucell_plan_destroy(p);
-                return fail(AUCELL_ERR_UNSUPPORTED,
-                            "the weights of one regulon span more than ~45 orders of magnitude; cannot guarantee 1e-6");
-            }
-            acc_parts[r] = (uint8_t)parts;
-            for (int k = 0; k < parts; ++k) acc_scale.push_back(std::ldexp(1.0, -(s1 + k * (B - 1))));
-            for (int64_t k = b; k < e; ++k) {
-                double res = h_reg_weights[k];
-                for (int l = 0; l < parts; ++l) {
-                    const int sl = s1 + l * (B - 1);
-                    const long long Wl = std::llrint(std::ldexp(res, sl));
-                    if (Wl != 0) ents.push_back({inv[h_reg_cols[k]], (uint32_t)(first + l), Wl});
-                    res -= std::ldexp((double)Wl, -sl);    // exact: Wl * 2^-sl is res rounded to a coarser grid
-                }
+                return qrc;
             }
         }
         p->n_acc = (int)acc_scale.size();
@@ -262,6 +307,59 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
             PCK(cudaMalloc(&p->d_tacc16, sizeof(uint16_t) * nalloc));
             PCK(cudaMemcpy(p->d_tacc16, t16.data(), sizeof(uint16_t) * nalloc, cudaMemcpyHostToDevice));
         }
+        // ---- ELL copy of T for aucell_tie_kernel: two (weighted) / four (unit) slots per gene, chained overflow ----
+        p->fast_ok = false;
+        if (tie_q && p->n_acc < (int)kTiePadU) {
+            PCK(cudaMalloc(&p->d_tie_stats, TIE_ST_N * sizeof(unsigned long long)));
+            PCK(cudaMemset(p->d_tie_stats, 0, TIE_ST_N * sizeof(unsigned long long)));
+            if (p->weighted) {
+                std::vector<uint4> ell((size_t)n_genes);
+                std::vector<uint2> xw;
+                for (int64_t g = 0; g < n_genes; ++g) {
+                    const uint32_t b = tptr[g], e = tptr[g + 1], len = e - b;
+                    uint4 row = make_uint4(0u, 0u, 0u, 0u);
+                    if (len >= 1) { row.x = (uint32_t)tw[b]; row.y = tacc[b] * 8u; }
+                    if (len == 2) { row.z = (uint32_t)tw[b + 1]; row.w = tacc[b + 1] * 8u; }
+                    if (len > 2) {
+                        row.y |= 0x80000000u;
+                        row.z = (uint32_t)xw.size();
+                        row.w = len - 1;
+                        for (uint32_t k = b + 1; k < e; ++k) xw.push_back(make_uint2((uint32_t)tw[k], tacc[k] * 8u));
+                    }
+                    ell[(size_t)g] = row;
+                }
+                if (xw.empty()) xw.push_back(make_uint2(0u, 0u));
+                PCK(cudaMalloc(&p->d_ell_w, sizeof(uint4) * (size_t)n_genes));
+                PCK(cudaMemcpy(p->d_ell_w, ell.data(), sizeof(uint4) * (size_t)n_genes, cudaMemcpyHostToDevice));
+                PCK(cudaMalloc(&p->d_xw, sizeof(uint2) * xw.size()));
+                PCK(cudaMemcpy(p->d_xw, xw.data(), sizeof(uint2) * xw.size(), cudaMemcpyHostToDevice));
+                p->tie_L = tieL;
+            } else {
+                std::vector<uint2> ell((size_t)n_genes);
+                std::vector<uint16_t> xu;
+                for (int64_t g = 0; g < n_genes; ++g) {
+                    const uint32_t b = tptr[g], e = tptr[g + 1], len = e - b;
+                    uint32_t s4[4] = {kTiePadU, kTiePadU, kTiePadU, kTiePadU};
+                    for (uint32_t k = 0; k < std::min<uint32_t>(len, 4u); ++k) s4[k] = tacc[b + k];
+                    uint2 row = make_uint2(s4[0] | (s4[1] << 16), s4[2] | (s4[3] << 16));
+                    if (len - 2 > 65535u && len > 4) { xu.assign((size_t)1 << 31, 0); break; }   // (never: n_acc < 32767)
+                    if (len > 4) {
+                        row.y = 0x80000000u | (uint32_t)xu.size();
+                        xu.push_back((uint16_t)(len - 2));
+                        for (uint32_t k = b + 2; k < e; ++k) xu.push_back((uint16_t)tacc[k]);
+                    }
+                    ell[(size_t)g] = row;
+                }
+                if (xu.empty()) xu.push_back(0);
+                if (xu.size() < ((size_t)1 << 31) && nT < ((size_t)1 << 31)) {
+                    PCK(cudaMalloc(&p->d_ell_u, sizeof(uint2) * (size_t)n_genes));
+                    PCK(cudaMemcpy(p->d_ell_u, ell.data(), sizeof(uint2) * (size_t)n_genes, cudaMemcpyHostToDevice));
+                    PCK(cudaMalloc(&p->d_xu, sizeof(uint16_t) * xu.size()));
+                    PCK(cudaMemcpy(p->d_xu, xu.data(), sizeof(uint16_t) * xu.size(), cudaMemcpyHostToDevice));
+                }
+            }
+            p->fast_ok = p->weighted ? p->d_ell_w != nullptr : p->d_ell_u != nullptr;
+        }
         const size_t nacc = std::max<size_t>(acc_scale.size(), 1);
         acc_scale.resize(nacc, 1.0);
         PCK(cudaMalloc(&p->d_acc_first, sizeof(int32_t) * n_regulons));
@@ -287,6 +385,11 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_tptr);
     cudaFree(p->d_tent);
     cudaFree(p->d_tacc16);
+    cudaFree(p->d_ell_w);
+    cudaFree(p->d_xw);
+    cudaFree(p->d_ell_u);
+    cudaFree(p->d_xu);
+    cudaFree(p->d_tie_stats);
     cudaFree(p->d_acc_first);
     cudaFree(p->d_acc_parts);
     cudaFree(p->d_acc_scale);
@@ -317,6 +420,25 @@ int aucell_plan_path_stats(const aucell_plan_t* p, uint64_t* out5, int reset) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out5, p->d_stats, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (reset) CK(cudaMemset(p->d_stats, 0, 8 * sizeof(unsigned long long)));
+    return AUCELL_OK;
+}
+
+int aucell_plan_set_fast_path(aucell_plan_t* p, int enable, int* out_available) {
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    p->fast_enabled = enable != 0;
+    if (out_available) *out_available = p->fast_ok ? 1 : 0;
+    return AUCELL_OK;
+}
+
+int aucell_plan_fast_stats(const aucell_plan_t* p, uint64_t* out8, int reset) {
+    if (!p || !out8) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    for (int k = 0; k < TIE_ST_N; ++k) out8[k] = 0;
+    if (!p->d_tie_stats) return AUCELL_OK;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out8, p->d_tie_stats, TIE_ST_N * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(p->d_tie_stats, 0, TIE_ST_N * sizeof(unsigned long long)));
     return AUCELL_OK;
 }
 
@@ -394,6 +516,18 @@ int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int
 }
 
 // ---- host-buffer streaming pipeline ------------------------------------------------------------------
+// Inside the chunk loops a failed CUDA call must not return at once: earlier chunks still have copies in flight that
+// read the caller's arrays and write h_out_auc.  CKB records the error and breaks; every exit then passes the loop
+// that synchronises the slot streams.
+#define CKB(call)                                                         \
+    {                                                                     \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) {                                          \
+            rc = fail_cuda(e_, #call, __LINE__);                          \
+            break;                                                        \
+        }                                                                 \
+    }
+
 namespace {
 
 constexpr int kHostSlots = 4;
@@ -561,12 +695,12 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         const int64_t nc = c1 - c0;
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
-        CK(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
+        CKB(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
         h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1) + ne * (int64_t)(sizeof(float) + (idx16 ? 2 : 4));
         d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         if (ne > 0) {
             if (idx16) {
-                if (s.idx_pending) CK(cudaEventSynchronize(s.idx_done));      // staging buffer free again
+                if (s.idx_pending) CKB(cudaEventSynchronize(s.idx_done));      // staging buffer free again
                 s.idx_pending = false;
                 const auto t0 = std::chrono::steady_clock::now();
                 if (!narrow_indices(h_indices + e0, s.pin_idx, ne, n_threads)) {
@@ -576,13 +710,13 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
                 narrow_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
                 narrow_n += ne;
                 ++narrow_chunks;
-                CK(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, s.st));
-                CK(cudaEventRecord(s.idx_done, s.st));
+                CKB(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, s.st));
+                CKB(cudaEventRecord(s.idx_done, s.st));
                 s.idx_pending = true;
             } else {
-                CK(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+                CKB(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
             }
-            CK(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
+            CKB(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
         }
         // the kernel indexes indices/data with the absolute offsets of h_indptr: shift the bases
         if (idx16)
@@ -605,8 +739,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
             const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - rate_t0).count();
             if (ns > (double)rate_n / 4.5) idx16 = false;        // < 4.5 G entries/s
         }
-        CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
-        if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        CKB(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+        if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
     for (auto& s : p->host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
@@ -646,13 +780,13 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
         double* d_auc = reinterpret_cast<double*>(s.buf + o_auc);
         int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
         const int64_t nc = std::min(n_cells, c0 + chunk_cells) - c0;
-        CK(cudaMemcpyAsync(d_vals, h_expr + c0 * row_stride, sizeof(float) * nc * row_stride, cudaMemcpyHostToDevice, s.st));
+        CKB(cudaMemcpyAsync(d_vals, h_expr + c0 * row_stride, sizeof(float) * nc * row_stride, cudaMemcpyHostToDevice, s.st));
         p->last_h2d_bytes += (int64_t)sizeof(float) * nc * row_stride;
         p->last_d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         rc = aucell_dense_f32(p, d_vals, nc, row_stride, d_auc, d_nnz, s.st);
         if (rc) break;
-        CK(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
-        if (h_out_nnz) CK(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        CKB(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+        if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
     for (auto& s : p->host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);

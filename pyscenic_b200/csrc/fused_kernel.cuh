@@ -104,6 +104,9 @@ struct FusedArgs {
     void* scratch_key;
     void* scratch_pos;
     int scratch_cap;
+    // to-do list (nullable): rank only the cells todo[0 .. *todo_n) -- what aucell_tie_kernel left over
+    const int32_t* todo;
+    const int32_t* todo_n;
     // path statistics (nullable): [0] cells, [1] general: too many entries, [2] general: negatives below the
     // cutoff, [3] general: crowded sub-bucket, [4] cells that needed zeros below the cutoff
     unsigned long long* stats;
@@ -665,7 +668,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     }
     __syncthreads();
 
-    for (int64_t cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x) {
+    const int64_t n_iter = a.todo != nullptr ? (int64_t)*a.todo_n : a.n_cells;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        const int64_t cell = a.todo != nullptr ? (int64_t)a.todo[it] : it;
         using IdxT = typename IdxOf<IN>::type;
         RowView<ValT, IdxT> row;
         if (IN != IN_DENSE) {

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
+#include <type_traits>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +21,7 @@
 #include <vector>
 
 #include "fused_kernel.cuh"
+#include "tie_kernel.cuh"
 
 namespace aucell_host {
 
@@ -91,6 +94,16 @@ struct aucell_plan {
     double* d_acc_scale = nullptr;
     double* d_reg_max_auc = nullptr;
     unsigned long long* d_stats = nullptr;   // path statistics of the fused kernel (5 counters)
+    // tie-class kernel (tie_kernel.cuh): ELL regulon table, u32 limb accumulators.  Built when the plan qualifies
+    // (16-bit positions, non-negative weights of bounded range); aucell_fused_kernel then takes only the to-do list.
+    bool fast_ok = false;
+    bool fast_enabled = true;                // aucell_plan_set_fast_path
+    int tie_L = 0;                           // weighted: products are split at this bit
+    uint4* d_ell_w = nullptr;
+    uint2* d_xw = nullptr;
+    uint2* d_ell_u = nullptr;
+    uint16_t* d_xu = nullptr;
+    unsigned long long* d_tie_stats = nullptr;   // [TIE_ST_N]
     // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
     struct HostSlot {
         cudaStream_t st = nullptr;
@@ -146,6 +159,100 @@ inline int get_scratch(const aucell_plan* p, cudaStream_t st, int key_bytes, int
     return AUCELL_OK;
 }
 
+// to-do list of the tie-class kernel: [0] counter (int32), list from byte 16 on; one per stream, grown on demand
+inline int get_todo(const aucell_plan* p, cudaStream_t st, int64_t n_cells, int32_t** todo, int32_t** todo_n) {
+    const size_t need = 16 + sizeof(int32_t) * (size_t)n_cells;
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto& slot = p->scratch[{st, -1}];
+    if (slot.second < need) {
+        if (slot.first) cudaFree(slot.first);
+        slot = {nullptr, 0};
+        void* ptr = nullptr;
+        cudaError_t e = cudaMalloc(&ptr, need);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(todo)", __LINE__);
+        slot = {ptr, need};
+    }
+    *todo_n = reinterpret_cast<int32_t*>(slot.first);
+    *todo = reinterpret_cast<int32_t*>((char*)slot.first + 16);
+    return AUCELL_OK;
+}
+
+// ---- tie-class kernel -----------------------------------------------------------------------------------------
+struct TieLayout { int group_stride, groups, smem; };
+
+// shared-memory carve-up of aucell_tie_kernel; fills the offsets of `a`
+inline TieLayout tie_layout(const aucell_plan* p, TieArgs& a, int cap) {
+    const int ip_bytes = align16(((p->n_genes + 7) / 8) * 16);
+    int off = 0;
+    a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16);
+    a.o_wpre = off; off = align16(off + p->n_words * 2);
+    a.o_rep = off; off = align16(off + kTieNB * 4);
+    a.o_code = off; off = align16(off + kTieNB);
+    a.o_bpp = off; off = align16(off + cap * 2);
+    a.o_bpc = off; off = align16(off + cap);
+    a.o_cnt = off; off = align16(off + kTieD * kTG * 2);
+    a.o_fix = off; off = align16(off + kTieFix * 8);
+    a.o_acc = off; off = align16(off + a.acc_words * 4);
+    a.o_misc = off; off = align16(off + 256);
+    TieLayout L;
+    L.group_stride = off;
+    const int64_t room = p->smem_optin - ip_bytes;
+    L.groups = (int)std::max<int64_t>(0, std::min<int64_t>(kTieMaxGroups, room / off));
+    L.smem = ip_bytes + L.groups * off;
+    a.off_group0 = ip_bytes;
+    a.group_stride = off;
+    a.groups = L.groups;
+    a.cap = cap;
+    return L;
+}
+
+inline int tie_cap() {
+    const char* env = getenv("AUCELL_B200_TIE_CAP");
+    int cap = env && *env ? atoi(env) : kTieMaxCap;
+    return std::max(256, std::min(kTieMaxCap, cap)) & ~15;
+}
+
+// Launch aucell_tie_kernel over all cells; cells it leaves are listed in *todo (count in **todo_n, device memory).
+template <int IN>
+int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices, const void* data, int64_t n_cells,
+               double* out_auc, int32_t* out_nnz, cudaStream_t st, int32_t** todo, int32_t** todo_n, bool* launched) {
+    *launched = false;
+    TieArgs a;
+    memset(&a, 0, sizeof a);
+    a.acc_words = p->weighted ? 2 * p->n_acc : p->n_acc;
+    const TieLayout L = tie_layout(p, a, tie_cap());
+    if (L.groups < 1) return AUCELL_OK;            // does not fit: the caller runs aucell_fused_kernel on everything
+    int rc = get_todo(p, st, n_cells, todo, todo_n);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(*todo_n, 0, sizeof(int32_t), st));
+    a.indptr = indptr; a.indices = indices; a.data = data;
+    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
+    a.wpt = (p->n_words + kTG - 1) / kTG;
+    a.cutoff = (int)p->rank_cutoff;
+    a.inv_perm = p->d_inv_perm16;
+    a.ell_w = p->d_ell_w; a.xw = p->d_xw; a.ell_u = p->d_ell_u; a.xu = p->d_xu;
+    a.L = p->tie_L;
+    a.n_regulons = p->n_regulons;
+    a.acc_first = p->d_acc_first; a.acc_parts = p->d_acc_parts; a.acc_scale = p->d_acc_scale;
+    a.max_auc = p->d_reg_max_auc;
+    a.out_auc = out_auc; a.out_nnz = out_nnz;
+    a.todo = *todo; a.todo_n = *todo_n;
+    a.stats = p->d_tie_stats;
+    const int grid = (int)std::min<int64_t>(p->sm_count, (n_cells + L.groups - 1) / L.groups);
+#define LAUNCH_TIE(UNIT)                                                                          \
+    do {                                                                                          \
+        auto k = aucell_tie_kernel<IN, UNIT>;                                                     \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));         \
+        k<<<grid, kTG * L.groups, L.smem, st>>>(a);                                               \
+    } while (0)
+    if (p->weighted) LAUNCH_TIE(false); else LAUNCH_TIE(true);
+#undef LAUNCH_TIE
+    launch_counter().fetch_add(1);
+    CK(cudaGetLastError());
+    *launched = true;
+    return AUCELL_OK;
+}
+
 // ---- fused AUCell kernel ------------------------------------------------------------------------------------
 // resident CTAs per SM of a kernel (registers, shared memory, threads): the persistent grid is a multiple of it
 template <typename K>
@@ -188,6 +295,10 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     if (IN != IN_DENSE && !indptr) return fail(AUCELL_ERR_INVALID, "CSR input: NULL indptr");
     if (IN == IN_CSR16 && !p->pos16) return fail(AUCELL_ERR_INVALID, "uint16 column indices need n_genes <= 65535");
     if (!out_auc) return fail(AUCELL_ERR_INVALID, "out_auc is NULL");
+    // AUCell proper has rank_cutoff < n_genes; larger cutoffs (cisTarget on column-selected rankings) exist only for
+    // aucell_from_rankings_u32.  Here they would truncate the 16-bit multipliers of the scatter queue.
+    if (p->rank_cutoff > p->n_genes)
+        return fail(AUCELL_ERR_INVALID, "rank_cutoff > n_genes: only aucell_from_rankings_u32 accepts such plans");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
@@ -222,6 +333,17 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.stats = p->d_stats;
     a.scratch_cap = next_pow2(p->n_genes);
+    // Count-like cells go through the tie-class kernel; what it leaves (long rows, negative / NaN values, continuous
+    // values) comes back as a to-do list for the kernel below.
+    if constexpr (IN != IN_DENSE && std::is_same<ValT, float>::value) {
+        if (p->fast_ok && p->fast_enabled && n_cells < (int64_t)INT32_MAX) {
+            bool launched = false;
+            int32_t *todo = nullptr, *todo_n = nullptr;
+            int rc = launch_tie<IN>(p, indptr, indices, data, n_cells, out_auc, out_nnz, st, &todo, &todo_n, &launched);
+            if (rc) return rc;
+            if (launched) { a.todo = todo; a.todo_n = todo_n; }
+        }
+    }
     if constexpr (IN == IN_CSR16) {       // 16-bit indices imply 16-bit positions: one instantiation
         return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
     } else {

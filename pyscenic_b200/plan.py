@@ -208,6 +208,21 @@ class AUCellPlan:
         keys = ("cells", "general_too_many_entries", "general_negatives", "general_crowded_bin", "cells_with_zeros")
         return dict(zip(keys, [int(x) for x in buf]))
 
+    def set_fast_path(self, enable: bool) -> bool:
+        """Route CSR float32 calls through the tie-class kernel (default) or send every cell to the general kernel.
+        Returns whether the plan qualifies for the tie-class kernel at all (see aucell_plan_set_fast_path)."""
+        avail = ctypes.c_int(0)
+        _native.check(self._lib.aucell_plan_set_fast_path(self._handle, 1 if enable else 0, ctypes.byref(avail)))
+        return bool(avail.value)
+
+    def fast_stats(self, reset: bool = True) -> dict:
+        """Cells per outcome of the tie-class kernel since the last reset (see aucell_plan_fast_stats)."""
+        buf = (ctypes.c_uint64 * 8)()
+        _native.check(self._lib.aucell_plan_fast_stats(self._handle, buf, 1 if reset else 0))
+        keys = ("ranked", "handed_long_row", "handed_negative_or_nan", "handed_duplicate_column", "handed_mixed_bin",
+                "handed_tail_overflow", "handed_skipped")
+        return dict(zip(keys, [int(x) for x in buf][:7]))
+
     def last_host_bytes(self):
         """(host-to-device, device-to-host) bytes the last ``*_host`` call moved (see aucell_plan_last_host_bytes)."""
         buf = (ctypes.c_int64 * 2)()

@@ -36,15 +36,30 @@ def regulon_specificity_scores(auc_mtx: pd.DataFrame, cell_type_series: pd.Serie
     regulons = list(auc_mtx.columns)
     n_cells, n_reg = auc_mtx.shape
     assert len(cell_type_series) == n_cells, "one cell type label per row of the AUC matrix"
-    codes = pd.Categorical(cell_type_series.to_numpy(), categories=cell_types).codes.astype(np.int32)
-    assert (codes >= 0).all(), "cell type labels must not be missing"
-    counts = np.bincount(codes, minlength=len(cell_types)).astype(np.int64)
+    # a missing label is a "type" of its own in the reference's loop whose indicator (series == NaN) is all False:
+    # its row comes out NaN, and its cells still count in every regulon's total.  Here they form a dummy type whose
+    # row is dropped.
+    valid_types = [t for t in cell_types if not pd.isna(t)]
+    codes = pd.Categorical(cell_type_series.to_numpy(), categories=valid_types).codes.astype(np.int32)
+    n_missing = int((codes < 0).sum())
+    n_types = len(valid_types) + (1 if n_missing else 0)
+    codes[codes < 0] = len(valid_types)
+    if n_types == 0 or n_cells == 0:
+        return pd.DataFrame(data=np.empty((len(cell_types), n_reg), dtype=np.float32), index=cell_types, columns=regulons)
+    counts = np.bincount(codes, minlength=n_types).astype(np.int64)
     dev = torch.device("cuda", device)
     a = torch.from_numpy(np.ascontiguousarray(auc_mtx.to_numpy(), dtype=np.float64)).to(dev)
     lab = torch.from_numpy(codes).to(dev)
-    out = torch.empty((len(cell_types), n_reg), dtype=torch.float64, device=dev)
+    out = torch.empty((n_types, n_reg), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream(dev).cuda_stream
-        _native.check(lib.aucell_rss_f64(device, a.data_ptr(), n_cells, n_reg, n_reg, lab.data_ptr(), len(cell_types),
+        _native.check(lib.aucell_rss_f64(device, a.data_ptr(), n_cells, n_reg, n_reg, lab.data_ptr(), n_types,
                                          counts.ctypes.data_as(ctypes.c_void_p), out.data_ptr(), ctypes.c_void_p(st)))
-    return pd.DataFrame(data=out.cpu().numpy().astype(np.float32), index=cell_types, columns=regulons)
+    res = out.cpu().numpy().astype(np.float32)
+    rows = np.full((len(cell_types), n_reg), np.nan, dtype=np.float32)
+    k = 0
+    for i, t in enumerate(cell_types):
+        if not pd.isna(t):
+            rows[i] = res[k]
+            k += 1
+    return pd.DataFrame(data=rows, index=cell_types, columns=regulons)
