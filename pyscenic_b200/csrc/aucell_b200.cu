@@ -309,28 +309,32 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
         }
         // ---- ELL copy of T for aucell_tie_kernel: two (weighted) / four (unit) slots per gene, chained overflow ----
         p->fast_ok = false;
-        if (tie_q && p->n_acc < (int)kTiePadU) {
+        if (tie_q && p->n_acc + 32 < (int)kTiePadU) {
             PCK(cudaMalloc(&p->d_tie_stats, TIE_ST_N * sizeof(unsigned long long)));
             PCK(cudaMemset(p->d_tie_stats, 0, TIE_ST_N * sizeof(unsigned long long)));
             if (p->weighted) {
-                std::vector<uint4> ell((size_t)n_genes);
+                std::vector<uint4> ell(2 * (size_t)n_genes);
                 std::vector<uint2> xw;
                 for (int64_t g = 0; g < n_genes; ++g) {
                     const uint32_t b = tptr[g], e = tptr[g + 1], len = e - b;
-                    uint4 row = make_uint4(0u, 0u, 0u, 0u);
-                    if (len >= 1) { row.x = (uint32_t)tw[b]; row.y = tacc[b] * 8u; }
-                    if (len == 2) { row.z = (uint32_t)tw[b + 1]; row.w = tacc[b + 1] * 8u; }
-                    if (len > 2) {
-                        row.y |= 0x80000000u;
-                        row.z = (uint32_t)xw.size();
-                        row.w = len - 1;
-                        for (uint32_t k = b + 1; k < e; ++k) xw.push_back(make_uint2((uint32_t)tw[k], tacc[k] * 8u));
+                    // empty slots: W = 0 into one of the 32 dummy accumulator pairs behind the real ones
+                    const uint32_t pad = (uint32_t)(2 * p->n_acc + 2 * (g & 31)) * 4u;
+                    uint32_t sw[4] = {0u, 0u, 0u, 0u}, so[4] = {pad, pad, pad, pad};
+                    const uint32_t direct = len > 4 ? 3u : len;
+                    // byte offset of an accumulator's low limb: the limbs swap places every 16 accumulators (tie_slot_w)
+                    auto lo_off = [](uint32_t acc) { return acc * 8u + ((acc & 16u) ? 4u : 0u); };
+                    for (uint32_t k = 0; k < direct; ++k) { sw[k] = (uint32_t)tw[b + k]; so[k] = lo_off(tacc[b + k]); }
+                    if (len > 4) {
+                        sw[3] = (uint32_t)xw.size();
+                        so[3] = 0x80000000u | (len - 3);
+                        for (uint32_t k = b + 3; k < e; ++k) xw.push_back(make_uint2((uint32_t)tw[k], lo_off(tacc[k])));
                     }
-                    ell[(size_t)g] = row;
+                    ell[2 * (size_t)g] = make_uint4(sw[0], so[0], sw[1], so[1]);
+                    ell[2 * (size_t)g + 1] = make_uint4(sw[2], so[2], sw[3], so[3]);
                 }
                 if (xw.empty()) xw.push_back(make_uint2(0u, 0u));
-                PCK(cudaMalloc(&p->d_ell_w, sizeof(uint4) * (size_t)n_genes));
-                PCK(cudaMemcpy(p->d_ell_w, ell.data(), sizeof(uint4) * (size_t)n_genes, cudaMemcpyHostToDevice));
+                PCK(cudaMalloc(&p->d_ell_w, sizeof(uint4) * ell.size()));
+                PCK(cudaMemcpy(p->d_ell_w, ell.data(), sizeof(uint4) * ell.size(), cudaMemcpyHostToDevice));
                 PCK(cudaMalloc(&p->d_xw, sizeof(uint2) * xw.size()));
                 PCK(cudaMemcpy(p->d_xw, xw.data(), sizeof(uint2) * xw.size(), cudaMemcpyHostToDevice));
                 p->tie_L = tieL;
@@ -339,7 +343,8 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
                 std::vector<uint16_t> xu;
                 for (int64_t g = 0; g < n_genes; ++g) {
                     const uint32_t b = tptr[g], e = tptr[g + 1], len = e - b;
-                    uint32_t s4[4] = {kTiePadU, kTiePadU, kTiePadU, kTiePadU};
+                    const uint32_t padu = (uint32_t)p->n_acc + (uint32_t)(g & 31);     // a dummy accumulator
+                    uint32_t s4[4] = {padu, padu, padu, padu};
                     for (uint32_t k = 0; k < std::min<uint32_t>(len, 4u); ++k) s4[k] = tacc[b + k];
                     uint2 row = make_uint2(s4[0] | (s4[1] << 16), s4[2] | (s4[3] << 16));
                     if (len - 2 > 65535u && len > 4) { xu.assign((size_t)1 << 31, 0); break; }   // (never: n_acc < 32767)
@@ -368,6 +373,13 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
         PCK(cudaMemcpy(p->d_acc_parts, acc_parts.data(), n_regulons, cudaMemcpyHostToDevice));
         PCK(cudaMalloc(&p->d_acc_scale, sizeof(double) * nacc));
         PCK(cudaMemcpy(p->d_acc_scale, acc_scale.data(), sizeof(double) * nacc, cudaMemcpyHostToDevice));
+        {
+            std::vector<double> scale0((size_t)n_regulons, 1.0);
+            for (int r = 0; r < n_regulons; ++r)
+                if (acc_first[r] >= 0) scale0[r] = acc_scale[(size_t)acc_first[r]];
+            PCK(cudaMalloc(&p->d_scale0, sizeof(double) * n_regulons));
+            PCK(cudaMemcpy(p->d_scale0, scale0.data(), sizeof(double) * n_regulons, cudaMemcpyHostToDevice));
+        }
         PCK(cudaMalloc(&p->d_reg_max_auc, sizeof(double) * n_regulons));
         PCK(cudaMemcpy(p->d_reg_max_auc, h_reg_max_auc, sizeof(double) * n_regulons, cudaMemcpyHostToDevice));
     }
@@ -390,6 +402,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_ell_u);
     cudaFree(p->d_xu);
     cudaFree(p->d_tie_stats);
+    cudaFree(p->d_scale0);
     cudaFree(p->d_acc_first);
     cudaFree(p->d_acc_parts);
     cudaFree(p->d_acc_scale);

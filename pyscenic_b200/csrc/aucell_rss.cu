@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kRssThreads) rss_finish_kernel(const double* _
         S += o[1];
     }
     const double js = 0.5 * (0.6931471805599453 * (1.0 - P) + S);
-    out[(int64_t)t * n_reg + r] = 1.0 - sqrt(fmax(js, 0.0));   // rounding can leave js = -1e-17 when p == q; NaN passes through
+    out[(int64_t)t * n_reg + r] = 1.0 - sqrt(js < 0.0 ? 0.0 : js);   // rounding can leave js = -1e-17 when p == q; NaN (all-zero regulon) passes through
 }
 
 }  // namespace

@@ -24,4 +24,12 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+// `sum`, or 1.0 when sum is +0.0 -- through the bit pattern, so that the compiler cannot fold the substitution back
+// into the division it guards (a zero dividend sends DDIV down its out-of-line special-case path for the whole warp;
+// the caller selects 0.0 for those lanes afterwards).  Sums here are never negative zero.
+__device__ __forceinline__ double nonzero_numerator(double sum) {
+    const long long b = __double_as_longlong(sum);
+    return __longlong_as_double(b | (b == 0ll ? 0x3FF0000000000000ll : 0ll));
+}
+
 }  // namespace aucell

@@ -352,7 +352,9 @@ __device__ __forceinline__ void write_aucs_packed(const GeneTableDev& t, uint32_
                 }
                 acc_lo[f + k] = 0u;
             }
-            res = __ddiv_rn(sum, __ldg(t.max_auc + r));
+            // (a zero numerator sends DDIV down its out-of-line special-case path for the whole warp)
+            const double q = __ddiv_rn(nonzero_numerator(sum), __ldg(t.max_auc + r));
+            res = sum == 0.0 ? 0.0 : q;
         }
         out[r] = res;
     }
@@ -1116,7 +1118,9 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                         sum = (double)acc_lo[my_first];
                     }
                     acc_lo[my_first] = 0u;
-                    res = __ddiv_rn(sum, my_max_auc);
+                    // (a zero numerator sends DDIV down its out-of-line special-case path for the whole warp)
+                    const double q = __ddiv_rn(nonzero_numerator(sum), my_max_auc);
+                    res = sum == 0.0 ? 0.0 : q;
                 }
                 a.out_auc[cell * (int64_t)a.tab.n_regulons + tid] = res;
             }

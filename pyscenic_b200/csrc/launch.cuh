@@ -104,6 +104,7 @@ struct aucell_plan {
     uint2* d_ell_u = nullptr;
     uint16_t* d_xu = nullptr;
     unsigned long long* d_tie_stats = nullptr;   // [TIE_ST_N]
+    double* d_scale0 = nullptr;                  // [R] acc_scale of every regulon's first accumulator
     // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
     struct HostSlot {
         cudaStream_t st = nullptr;
@@ -172,7 +173,7 @@ inline int get_todo(const aucell_plan* p, cudaStream_t st, int64_t n_cells, int3
         if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(todo)", __LINE__);
         slot = {ptr, need};
     }
-    *todo_n = reinterpret_cast<int32_t*>(slot.first);
+    *todo_n = reinterpret_cast<int32_t*>(slot.first);          // [0] counter, [1..2] value range (tie_range_kernel)
     *todo = reinterpret_cast<int32_t*>((char*)slot.first + 16);
     return AUCELL_OK;
 }
@@ -184,16 +185,16 @@ struct TieLayout { int group_stride, groups, smem; };
 inline TieLayout tie_layout(const aucell_plan* p, TieArgs& a, int cap) {
     const int ip_bytes = align16(((p->n_genes + 7) / 8) * 16);
     int off = 0;
-    a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16);
+    a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16 + 16);     // + the spare word invalid lanes OR into
     a.o_wpre = off; off = align16(off + p->n_words * 2);
-    a.o_rep = off; off = align16(off + kTieNB * 4);
+    a.o_rep = off; off = align16(off + (kTieNB + 4) * 4);                   // + the spare bin
     a.o_code = off; off = align16(off + kTieNB);
-    a.o_bpp = off; off = align16(off + cap * 2);
-    a.o_bpc = off; off = align16(off + cap);
-    a.o_cnt = off; off = align16(off + kTieD * kTG * 2);
+    a.o_bpp = off; off = align16(off + (cap + 1) * 2);                      // + the spare slot
+    a.o_bpc = off; off = align16(off + cap + 1);
+    a.o_cnt = off; off = align16(off + kTieD * kTG * 4);
     a.o_fix = off; off = align16(off + kTieFix * 8);
     a.o_acc = off; off = align16(off + a.acc_words * 4);
-    a.o_misc = off; off = align16(off + 256);
+    a.o_misc = off; off = align16(off + kTieMiscWords * 4);
     TieLayout L;
     L.group_stride = off;
     const int64_t room = p->smem_optin - ip_bytes;
@@ -219,7 +220,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     *launched = false;
     TieArgs a;
     memset(&a, 0, sizeof a);
-    a.acc_words = p->weighted ? 2 * p->n_acc : p->n_acc;
+    a.acc_words = p->weighted ? 2 * p->n_acc + 64 : p->n_acc + 32;       // + 32 dummy accumulators (empty table slots)
     const TieLayout L = tie_layout(p, a, tie_cap());
     if (L.groups < 1) return AUCELL_OK;            // does not fit: the caller runs aucell_fused_kernel on everything
     int rc = get_todo(p, st, n_cells, todo, todo_n);
@@ -234,11 +235,15 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     a.L = p->tie_L;
     a.n_regulons = p->n_regulons;
     a.acc_first = p->d_acc_first; a.acc_parts = p->d_acc_parts; a.acc_scale = p->d_acc_scale;
+    a.scale0 = p->d_scale0;
+    a.range = reinterpret_cast<const uint32_t*>(*todo_n) + 1;
     a.max_auc = p->d_reg_max_auc;
     a.out_auc = out_auc; a.out_nnz = out_nnz;
     a.todo = *todo; a.todo_n = *todo_n;
     a.stats = p->d_tie_stats;
     const int grid = (int)std::min<int64_t>(p->sm_count, (n_cells + L.groups - 1) / L.groups);
+    tie_range_kernel<IN><<<1, 1024, 0, st>>>(indptr, n_cells, data, reinterpret_cast<uint32_t*>(*todo_n) + 1);
+    launch_counter().fetch_add(1);
 #define LAUNCH_TIE(UNIT)                                                                          \
     do {                                                                                          \
         auto k = aucell_tie_kernel<IN, UNIT>;                                                     \

@@ -13,11 +13,11 @@
 // barrier (bar.sync id, 128), so no phase ever waits for more than four warps.
 //
 // rank(g) = #{genes with a larger value} + #{genes with the same value at a smaller shuffled position}.  Per cell:
-//   P0  statistics      min / max of the positive values (float bits order like the values), #non-zero; negative or
-//                       NaN values, or more than `cap` entries: to-do list.
+//   P0  value range     of a sample of the whole matrix (tie_range_kernel, one small CTA before this kernel).  Cells with
+//                       more than `cap` entries, negative or NaN values: to-do list.
 //   P1  bitmap          A[pos] = 1 for every non-zero entry (one atomicOr each); rep[bin] = value bits, where
-//                       bin = (max - bits) >> shift maps the cell's own value range onto 1024 bins -- float bits are
-//                       piecewise linear in log2(value), so integer counts up to ~60 get a bin each.
+//                       bin = (max - bits) >> shift maps the sampled value range onto 512 bins -- float bits are
+//                       piecewise linear in log2(value), so integer counts up to ~30 get a bin each.
 //   P2  two scans       word prefix of A (position order for free: the j-th set bit is the j-th smallest position);
 //                       occupied bins -> dense class index, descending value; the (kTieD - 1) LOWEST values get a
 //                       class each, everything above them (few genes, many distinct values) is class 0, the tail.
@@ -30,7 +30,7 @@
 //                       W * (cutoff - rank) for every regulon holding the gene: the regulon table is ELL (two slots
 //                       per gene in one 128-bit load, chained overflow), accumulators are pairs of u32 limbs updated
 //                       with non-returning shared atomics (the product is split at bit L, so no carry is needed).
-//   P7  tail            all pairs over the (<= 256) tail entries: rank = #{(value, pos) before mine}.
+//   P7  tail            all pairs over the (<= 128) tail entries: rank = #{(value, pos) before mine}.
 //   P8  zeros           fewer positives than the cutoff: zeros fill the remaining ranks in position order.
 //   P9  out             out[cell, r] = (double(hi << L + lo) * 2^-s) / max_auc[r], coalesced.
 #pragma once
@@ -41,15 +41,18 @@
 
 namespace aucell {
 
-constexpr int kTG = 128;                // threads per cell group
+constexpr int kTG = 256;                // threads per cell group
 constexpr int kTGW = kTG / 32;
-constexpr int kTieNBLog = 10;
+constexpr int kTieNBLog = 9;
 constexpr int kTieNB = 1 << kTieNBLog;  // value bins over the cell's own range
-constexpr int kTieD = 32;               // value classes per cell (class 0 = tail)
-constexpr int kTieFix = 256;            // tail entries per cell
-constexpr int kTieMaxGroups = 6;        // cell groups per CTA
+constexpr int kTieD = 16;               // value classes per cell (class 0 = tail)
+constexpr int kTieFix = 128;            // tail entries per cell
+constexpr int kTieMaxGroups = 4;        // cell groups per CTA (1024 threads)
+constexpr int kTieP6 = 2;               // items per thread and pass of P6 (their table rows are loaded together)
+constexpr int kTieMiscWords = 128;      // per group: reductions, scan words, flags, chain list lengths
+constexpr int kTieU = 4;                // entries per thread and pass of the streaming loops (loads issued together)
 constexpr int kTieMaxCap = 4096;        // stored entries per cell (20-bit reciprocal in P3; u16 prefixes)
-constexpr uint32_t kTiePadU = 0x7FFFu;  // empty slot of a unit-weight table row
+constexpr uint32_t kTiePadU = 0x7FFFu;  // unit weights: accumulator indices stay below this (bit 31 of a row flags a chain)
 
 // to-do reasons (statistics only)
 enum { TIE_ST_FAST = 0, TIE_ST_LONG = 1, TIE_ST_BADVAL = 2, TIE_ST_DUP = 3, TIE_ST_MIXED = 4, TIE_ST_TAIL = 5,
@@ -63,7 +66,8 @@ struct TieArgs {
     int n_genes, n_words, wpt;          // wpt = ceil(n_words / kTG)
     int cutoff;
     const uint16_t* inv_perm;           // [n_genes rounded up to 8]
-    const uint4* ell_w;                 // weighted: [n_genes] {W0, off0 | chain << 31, W1 or start, off1 or count}
+    const uint4* ell_w;                 // weighted: [2 * n_genes] four slots {W, off} per gene; a gene in more than
+                                        //           four regulons keeps three and {start, count | 1 << 31} of a chain
     const uint2* xw;                    //           chained slots {W, off}
     const uint2* ell_u;                 // unit weights: [n_genes] four uint16 accumulators, or two + chain
     const uint16_t* xu;                 //           chained: count, accumulators...
@@ -73,6 +77,8 @@ struct TieArgs {
     const int32_t* acc_first;           // [R] first accumulator of regulon r, -1 = invalid regulon
     const uint8_t* acc_parts;           // [R]
     const double* acc_scale;            // [n_acc]
+    const double* scale0;               // [R] acc_scale of the regulon's first accumulator
+    const uint32_t* range;              // [2] bits of the smallest / largest positive value of a sample (tie_range_kernel)
     const double* max_auc;              // [R]
     double* out_auc;
     int32_t* out_nnz;
@@ -86,11 +92,10 @@ struct TieArgs {
     int o_A, o_wpre, o_rep, o_code, o_bpp, o_bpc, o_cnt, o_fix, o_acc, o_misc;
 };
 
-__device__ __forceinline__ void group_bar(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kTG) : "memory");
-}
+// named barrier of one cell group (the builtin is convergent: the compiler reconverges the warp before it)
+__device__ __forceinline__ void group_bar(int id) { __barrier_sync_count((unsigned)id, (unsigned)kTG); }
 
-// exclusive scan over the kTG threads of a group; s_w: 4 words nobody else writes until two barriers later
+// exclusive scan over the kTG threads of a group; s_w: kTGW words nobody else writes until two barriers later
 __device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, uint32_t* s_w, int lane, int gw, int barid,
                                                     uint32_t& total) {
     uint32_t incl = v;
@@ -101,9 +106,14 @@ __device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, uint32_t* s_w, i
     }
     if (lane == 31) s_w[gw] = incl;
     group_bar(barid);
-    const uint4 w = *reinterpret_cast<const uint4*>(s_w);
-    const uint32_t off = (gw > 0 ? w.x : 0u) + (gw > 1 ? w.y : 0u) + (gw > 2 ? w.z : 0u);
-    total = w.x + w.y + w.z + w.w;
+    uint32_t off = 0u, tot = 0u;
+#pragma unroll
+    for (int k = 0; k < kTGW; k += 4) {
+        const uint4 w = *reinterpret_cast<const uint4*>(s_w + k);
+        off += (gw > k ? w.x : 0u) + (gw > k + 1 ? w.y : 0u) + (gw > k + 2 ? w.z : 0u) + (gw > k + 3 ? w.w : 0u);
+        tot += w.x + w.y + w.z + w.w;
+    }
+    total = tot;
     return off + incl - v;
 }
 
@@ -119,53 +129,120 @@ template <> struct TieVal<IN_CSR16_U8> {
     }
 };
 
-template <bool UNIT> struct TieRow { using type = uint4; };
-template <> struct TieRow<true> { using type = uint2; };
+// One gene's row of the regulon table: four slots.  Empty slots add zero to one of 32 dummy accumulators (picked by
+// the gene's position, so that a warp's empty slots spread over the banks): the hot loop has no branch per slot.
+template <bool UNIT> struct TieRow { uint4 a, b; };       // weighted: {W0, off0, W1, off1}, {W2, off2, W3, off3}
+template <> struct TieRow<true> { uint2 a; };             // unit weights: four uint16 accumulator indices
 
 template <bool UNIT>
-__device__ __forceinline__ typename TieRow<UNIT>::type tie_load_row(const TieArgs& a, unsigned pos) {
-    if constexpr (UNIT) return __ldg(a.ell_u + pos);
-    else return __ldg(a.ell_w + pos);
+__device__ __forceinline__ TieRow<UNIT> tie_load_row(const TieArgs& a, unsigned pos) {
+    TieRow<UNIT> r;
+    if constexpr (UNIT) {
+        r.a = __ldg(a.ell_u + pos);
+    } else {
+        r.a = __ldg(a.ell_w + 2 * pos);
+        r.b = __ldg(a.ell_w + 2 * pos + 1);
+    }
+    return r;
 }
 
-__device__ __forceinline__ void tie_slot_w(uint32_t* acc, uint32_t W, uint32_t off, uint32_t m, int L, uint32_t maskL) {
-    if (W) {
-        const unsigned long long p = (unsigned long long)W * m;
-        uint32_t* const at = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(acc) + off);
-        atomicAdd(at, (uint32_t)p & maskL);
-        atomicAdd(at + 1, (uint32_t)(p >> L));
+// acc[off] += low L bits of W * m, acc[off + 4] += the rest (non-returning shared atomics, no carry between them)
+__device__ __forceinline__ void tie_slot_w(uint32_t acc_s, uint32_t W, uint32_t off, uint32_t m, int L, uint32_t maskL) {
+    const unsigned long long p = (unsigned long long)W * m;
+    const uint32_t lo = (uint32_t)p & maskL;
+    const uint32_t hi = __funnelshift_r((uint32_t)p, (uint32_t)(p >> 32), L);
+    // the two limbs of an accumulator are neighbours; which comes first alternates every 16 accumulators (the table's
+    // offset points at the low limb), so that a warp's low-limb atomics spread over all 32 banks, not the even ones
+    asm volatile("red.shared.add.u32 [%0], %1;\n\tred.shared.add.u32 [%2], %3;" ::"r"(acc_s + off), "r"(lo), "r"((acc_s + off) ^ 4u), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void tie_slot_u(uint32_t acc_s, uint32_t a, uint32_t m) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + (a << 2)), "r"(m) : "memory");
+}
+
+// the chained slots of a gene that sits in more than four regulons
+template <bool UNIT>
+__device__ __forceinline__ void tie_apply_chain(const TieArgs& a, uint32_t acc_s, uint32_t start, uint32_t cnt,
+                                                uint32_t m, uint32_t maskL) {
+    if constexpr (UNIT) {
+#pragma unroll 1
+        for (uint32_t k = 1; k <= cnt; ++k) tie_slot_u(acc_s, __ldg(a.xu + start + k), m);
+    } else {
+#pragma unroll 1
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint2 sl = __ldg(a.xw + start + k);
+            tie_slot_w(acc_s, sl.x, sl.y, m, a.L, maskL);
+        }
     }
 }
 
-// add W * m to the accumulators of every regulon holding the gene whose table row is `row`
+// The direct slots of a row (branch-free).  Returns true when the row continues in a chain: start / cnt then say where.
 template <bool UNIT>
-__device__ __forceinline__ void tie_apply(const TieArgs& a, uint32_t* acc, const typename TieRow<UNIT>::type& row,
-                                          uint32_t m, uint32_t maskL) {
+__device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_s, const TieRow<UNIT>& row, uint32_t m,
+                                                 uint32_t maskL, uint32_t dummy, uint32_t& start, uint32_t& cnt) {
     if constexpr (UNIT) {
-        const uint32_t a0 = row.x & 0xFFFFu, a1 = row.x >> 16;
-        if (a0 != kTiePadU) atomicAdd(acc + a0, m);
-        if (a1 != kTiePadU) atomicAdd(acc + a1, m);
-        if (row.y >> 31) {
-            const uint32_t start = row.y & 0x7FFFFFFFu;
-            const uint32_t cnt = __ldg(a.xu + start);
-#pragma unroll 1
-            for (uint32_t k = 1; k <= cnt; ++k) atomicAdd(acc + __ldg(a.xu + start + k), m);
-        } else {
-            const uint32_t a2 = row.y & 0xFFFFu, a3 = row.y >> 16;
-            if (a2 != kTiePadU) atomicAdd(acc + a2, m);
-            if (a3 != kTiePadU) atomicAdd(acc + a3, m);
-        }
+        const bool chain = (row.a.y >> 31) != 0u;
+        tie_slot_u(acc_s, row.a.x & 0xFFFFu, m);
+        tie_slot_u(acc_s, row.a.x >> 16, m);
+        tie_slot_u(acc_s, chain ? dummy : (row.a.y & 0xFFFFu), m);
+        tie_slot_u(acc_s, chain ? dummy : (row.a.y >> 16), m);
+        start = row.a.y & 0x7FFFFFFFu;
+        cnt = 0u;                                          // (read from xu[start] by the consumer)
+        return chain;
     } else {
-        tie_slot_w(acc, row.x, row.y & 0x7FFFFFFFu, m, a.L, maskL);
-        if (row.y >> 31) {
-#pragma unroll 1
-            for (uint32_t k = 0; k < row.w; ++k) {
-                const uint2 s = __ldg(a.xw + row.z + k);
-                tie_slot_w(acc, s.x, s.y, m, a.L, maskL);
-            }
-        } else {
-            tie_slot_w(acc, row.z, row.w, m, a.L, maskL);
-        }
+        const bool chain = (row.b.w >> 31) != 0u;
+        tie_slot_w(acc_s, row.a.x, row.a.y, m, a.L, maskL);
+        tie_slot_w(acc_s, row.a.z, row.a.w, m, a.L, maskL);
+        tie_slot_w(acc_s, row.b.x, row.b.y, m, a.L, maskL);
+        tie_slot_w(acc_s, chain ? 0u : row.b.z, chain ? dummy : row.b.w, m, a.L, maskL);
+        start = row.b.z;
+        cnt = row.b.w & 0x7FFFFFFFu;
+        return chain;
+    }
+}
+
+// whole row at once (the rare phases: tail, zero fill)
+template <bool UNIT>
+__device__ __forceinline__ void tie_apply_full(const TieArgs& a, uint32_t acc_s, unsigned pos, uint32_t m,
+                                               uint32_t maskL, uint32_t dummy) {
+    const TieRow<UNIT> row = tie_load_row<UNIT>(a, pos);
+    uint32_t start, cnt;
+    if (tie_apply_direct<UNIT>(a, acc_s, row, m, maskL, dummy, start, cnt)) {
+        if constexpr (UNIT) cnt = __ldg(a.xu + start);
+        tie_apply_chain<UNIT>(a, acc_s, start, cnt, m, maskL);
+    }
+}
+
+constexpr int kTieChainCap = kTieNB * 4 / (kTGW * 8);      // chained rows a warp can defer (the list reuses rep[])
+
+// Value range of the matrix from a sample of its stored values (one small CTA before the main kernel):
+// range[0] = smallest, range[1] = largest positive value's bits among <= 64 k samples.  The main kernel maps this
+// range onto its kTieNB bins; a value outside it lands in an end bin, which the one-value-per-bin check covers.
+template <int IN>
+__global__ void __launch_bounds__(1024) tie_range_kernel(const int64_t* __restrict__ indptr, int64_t n_cells,
+                                                          const void* __restrict__ data, uint32_t* __restrict__ range) {
+    using VT = TieVal<IN>;
+    const int64_t e0 = indptr[0], total = indptr[n_cells] - e0;
+    const typename VT::type* const vals = reinterpret_cast<const typename VT::type*>(data) + e0;
+    uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+    const int64_t n_s = total < 65536 ? total : 65536;
+    for (int64_t k = threadIdx.x; k < n_s; k += 1024) {
+        const int64_t i = total <= 65536 ? k : (int64_t)(((unsigned __int128)k * (unsigned __int128)total) >> 16);
+        const uint32_t u = VT::bits(vals + i, 0);
+        const bool ps = (u << 1) != 0u && u <= 0x7F800000u;
+        umin = min(umin, ps ? u : 0xFFFFFFFFu);
+        umax = max(umax, ps ? u : 0u);
+    }
+    __shared__ uint32_t s_min, s_max;
+    if (threadIdx.x == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; }
+    __syncthreads();
+    umin = __reduce_min_sync(0xffffffffu, umin);
+    umax = __reduce_max_sync(0xffffffffu, umax);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, umin); atomicMax(&s_max, umax); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_max < s_min) { s_min = 0x3F800000u; s_max = 0x3F800000u; }      // no positive sample
+        range[0] = s_min;
+        range[1] = s_max;
     }
 }
 
@@ -173,7 +250,7 @@ template <int IN, bool UNIT>
 __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const TieArgs a) {
     using IdxT = typename IdxOf<IN>::type;
     using VT = TieVal<IN>;
-    using RowT = typename TieRow<UNIT>::type;
+    using RowT = TieRow<UNIT>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, grp = tid / kTG, gtid = tid % kTG, lane = tid & 31, gw = gtid >> 5;
 
@@ -185,26 +262,44 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         for (int i = tid; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(ip)[i] = __ldg(src + i);
     }
     unsigned char* const gb = smem + a.off_group0 + grp * a.group_stride;
-    uint32_t* const A = reinterpret_cast<uint32_t*>(gb + a.o_A);          // [n_words] occupied positions
+    uint32_t* const A = reinterpret_cast<uint32_t*>(gb + a.o_A);          // [n_words + pad] occupied positions
     uint16_t* const wpre = reinterpret_cast<uint16_t*>(gb + a.o_wpre);    // [n_words] set bits before the word
-    uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + a.o_rep);      // [kTieNB] value bits of the bin, 0 = empty
+    uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + a.o_rep);      // [kTieNB + 4] value bits of the bin, 0 = empty;
+                                                                          // from P6 on: the warps' chain lists
     uint8_t* const code_of = reinterpret_cast<uint8_t*>(gb + a.o_code);   // [kTieNB] class of the bin
-    uint16_t* const bpp = reinterpret_cast<uint16_t*>(gb + a.o_bpp);      // [cap] position of the j-th entry
-    uint8_t* const bpc = reinterpret_cast<uint8_t*>(gb + a.o_bpc);        // [cap] its class
-    uint32_t* const cnt32 = reinterpret_cast<uint32_t*>(gb + a.o_cnt);    // [kTieD][kTG] uint16 counters / bases
-    uint16_t* const cnt16 = reinterpret_cast<uint16_t*>(gb + a.o_cnt);
+    uint16_t* const bpp = reinterpret_cast<uint16_t*>(gb + a.o_bpp);      // [cap + 1] position of the j-th entry
+    uint8_t* const bpc = reinterpret_cast<uint8_t*>(gb + a.o_bpc);        // [cap + 1] its class
+    uint32_t* const cnt = reinterpret_cast<uint32_t*>(gb + a.o_cnt);      // [kTieD][kTG] counters, then bases
     uint2* const fix = reinterpret_cast<uint2*>(gb + a.o_fix);            // [kTieFix] (value bits, pos) of the tail
-    uint32_t* const acc = reinterpret_cast<uint32_t*>(gb + a.o_acc);
-    uint32_t* const misc = reinterpret_cast<uint32_t*>(gb + a.o_misc);    // [0..31] reductions (two parities),
-                                                                          // [32..35], [36..39] scan words,
-                                                                          // [40] tail count, [41] mixed-bin flag
+    uint32_t* const acc = reinterpret_cast<uint32_t*>(gb + a.o_acc);      // accumulators, then 32 dummies
+    uint32_t* const misc = reinterpret_cast<uint32_t*>(gb + a.o_misc);    // kTieMiscWords words, see kM* below
+    constexpr int kMScanA = 0;                 // [kTGW] scan words of P2
+    constexpr int kMScanB = kTGW;              // [kTGW] scan words of P5
+    constexpr int kMTail = 2 * kTGW;           // tail count
+    constexpr int kMMixed = 2 * kTGW + 1;      // two values in one class bin
+    constexpr int kMBad = 2 * kTGW + 2;        // negative / NaN value
+    constexpr int kMValid = 2 * kTGW + 3;      // entries P1 put into the bitmap
+    constexpr int kMChain = 2 * kTGW + 4;      // [kTGW] chain list lengths
+    static_assert(kMChain + kTGW <= kTieMiscWords && kTGW % 4 == 0, "misc layout");
     for (int i = gtid; i < a.acc_words; i += kTG) acc[i] = 0u;
+    if (gtid == 0) {                      // the dummy slot invalid lanes write to must always hold a valid (pos, class)
+        bpp[a.cap] = 0;
+        bpc[a.cap] = 0;
+    }
+    if (gtid < kTGW) misc[kMChain + gtid] = 0u;
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    uint2* const chain_list = reinterpret_cast<uint2*>(rep) + gw * kTieChainCap;
     __syncthreads();
 
     const int barid = 1 + grp;
-    const int n_genes = a.n_genes, n_words = a.n_words, cutoff = a.cutoff, R = a.n_regulons;
+    const int n_genes = a.n_genes, n_words = a.n_words, cutoff = a.cutoff, R = a.n_regulons, cap = a.cap;
+    const int dummy_word = (n_words + 3) & ~3;             // a word of A behind the bitmap: invalid lanes OR 0 into it
     const uint32_t maskL = UNIT ? 0u : ((1u << a.L) - 1u);
-    int par = 0;
+    // dummy accumulator of this lane (rows that continue in a chain; unit: index, weighted: byte offset)
+    const uint32_t dummy = UNIT ? (uint32_t)(a.acc_words - 32 + lane) : (uint32_t)(a.acc_words - 64 + 2 * lane) * 4u;
+    // value bits -> bin: (gmax - bits) >> shift, clamped (the range comes from a sample)
+    const uint32_t gmax = __ldg(a.range + 1);
+    const int shift = max(0, (32 - __clz((int)(gmax - __ldg(a.range)))) - kTieNBLog);
     int seen = 0, handed = 0;             // cells this group looked at / gave to the to-do list (group-uniform)
 
     auto hand_over = [&](int64_t cell, int why) {
@@ -215,9 +310,12 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         }
         ++handed;
     };
+    auto bin_of = [&](uint32_t u) -> uint32_t {
+        const int d = max((int)(gmax - u), 0);
+        return min((uint32_t)d >> shift, (uint32_t)(kTieNB - 1));
+    };
 
-    for (int64_t cell = (int64_t)blockIdx.x * a.groups + grp; cell < a.n_cells;
-         cell += (int64_t)gridDim.x * a.groups, par ^= 1) {
+    for (int64_t cell = (int64_t)blockIdx.x * a.groups + grp; cell < a.n_cells; cell += (int64_t)gridDim.x * a.groups) {
         // data this kernel does not suit (continuous values): stop looking, hand everything over
         if (seen >= 16 && handed * 8 >= seen * 7) {
             hand_over(cell, TIE_ST_SKIPPED);
@@ -226,84 +324,87 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         ++seen;
         const int64_t rb = __ldg(a.indptr + cell);
         const int64_t n64 = __ldg(a.indptr + cell + 1) - rb;
-        const bool fits = n64 >= 0 && n64 <= (int64_t)a.cap;
-        const int n = fits ? (int)n64 : 0;
+        if (n64 < 0 || n64 > (int64_t)cap) {
+            hand_over(cell, TIE_ST_LONG);
+            continue;
+        }
+        const int n = (int)n64;
+        const int iters = (n + kTieU * kTG - 1) / (kTieU * kTG);          // uniform trip count of the entry loops
         const IdxT* const cols = reinterpret_cast<const IdxT*>(a.indices) + rb;
         const typename VT::type* const vals = reinterpret_cast<const typename VT::type*>(a.data) + rb;
 
-        // ---------------- P0: statistics; clear the cell's working set -------------------------------------------
-        uint32_t umin = 0xFFFFFFFFu, umax = 0u, bad = 0u;
-        int npos = 0;
-#pragma unroll 4
-        for (int i = gtid; i < n; i += kTG) {
-            const uint32_t u = VT::bits(vals, i);
-            const bool nz = (u << 1) != 0u;                // +0.0 / -0.0 are not entries
-            const bool ng = u > 0x7F800000u;               // negative or NaN
-            const bool ps = nz && !ng;
-            bad |= (nz && ng) ? 1u : 0u;
-            npos += ps ? 1 : 0;
-            umin = min(umin, ps ? u : 0xFFFFFFFFu);
-            umax = max(umax, ps ? u : 0u);
-        }
-        umin = __reduce_min_sync(0xffffffffu, umin);
-        umax = __reduce_max_sync(0xffffffffu, umax);
-        npos = __reduce_add_sync(0xffffffffu, npos);
-        bad = __reduce_or_sync(0xffffffffu, bad);
-        uint32_t* const red = misc + par * 16;
-        if (lane == 0) *reinterpret_cast<uint4*>(red + gw * 4) = make_uint4(umin, umax, (uint32_t)npos, bad);
+        // ---------------- clear the cell's working set -----------------------------------------------------------
         {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = gtid; i < ((n_words + 3) >> 2); i += kTG) reinterpret_cast<uint4*>(A)[i] = z;
+            for (int i = gtid; i < ((n_words + 4) >> 2); i += kTG) reinterpret_cast<uint4*>(A)[i] = z;
 #pragma unroll
             for (int i = gtid; i < kTieNB / 4; i += kTG) reinterpret_cast<uint4*>(rep)[i] = z;
 #pragma unroll
-            for (int i = gtid; i < kTieD * kTG / 8; i += kTG) reinterpret_cast<uint4*>(cnt32)[i] = z;
-            if (gtid == 0) { misc[40] = 0u; misc[41] = 0u; }
+            for (int i = gtid; i < kTieD * kTG / 4; i += kTG) reinterpret_cast<uint4*>(cnt)[i] = z;
+            if (gtid == 0) *reinterpret_cast<uint4*>(misc + kMTail) = z;      // tail count, mixed, bad, valid
         }
         group_bar(barid);
-        {
-            const uint4 r0 = *reinterpret_cast<const uint4*>(red), r1 = *reinterpret_cast<const uint4*>(red + 4),
-                        r2 = *reinterpret_cast<const uint4*>(red + 8), r3 = *reinterpret_cast<const uint4*>(red + 12);
-            umin = min(min(r0.x, r1.x), min(r2.x, r3.x));
-            umax = max(max(r0.y, r1.y), max(r2.y, r3.y));
-            npos = (int)(r0.z + r1.z + r2.z + r3.z);
-            bad = r0.w | r1.w | r2.w | r3.w;
-        }
-        if (!fits || bad) {
-            hand_over(cell, fits ? TIE_ST_BADVAL : TIE_ST_LONG);
-            continue;
-        }
-        const uint32_t range = umax - umin;               // npos == 0: unused
-        const int shift = max(0, (32 - __clz((int)range)) - kTieNBLog);
 
         // ---------------- P1: position bitmap, one representative value per bin ----------------------------------
-#pragma unroll 4
-        for (int i = gtid; i < n; i += kTG) {
-            const uint32_t u = VT::bits(vals, i);
-            const unsigned col = (unsigned)cols[i];
-            if ((u << 1) != 0u && col < (unsigned)n_genes) {
-                const unsigned pos = ip[col];
-                rep[(umax - u) >> shift] = u;
-                atomicOr(&A[pos >> 5], 1u << (pos & 31));
+        // branch-free: lanes without an entry (past the row's end, explicit zeros, a column out of range) store into
+        // the spare bin rep[kTieNB] and OR 0 into the spare word behind the bitmap
+        {
+            uint32_t bad = 0u;
+            int nvalid = 0;
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int base = it * (kTieU * kTG) + gtid;
+                uint32_t u[kTieU];
+                unsigned col[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool in = base + k * kTG < n;
+                    u[k] = in ? VT::bits(vals, base + k * kTG) : 0u;
+                    col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool nz = (u[k] << 1) != 0u;                     // +0.0 / -0.0 are not entries
+                    const bool valid = nz && col[k] < (unsigned)n_genes;
+                    bad |= (nz && u[k] > 0x7F800000u) ? 1u : 0u;           // negative or NaN: not for this kernel
+                    nvalid += valid ? 1 : 0;
+                    const unsigned pos = ip[valid ? col[k] : 0u];
+                    rep[valid ? bin_of(u[k]) : (uint32_t)kTieNB] = u[k];
+                    atomicOr(&A[valid ? (pos >> 5) : (unsigned)dummy_word], valid ? (1u << (pos & 31)) : 0u);
+                }
+            }
+            nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+            bad = __reduce_or_sync(0xffffffffu, bad);
+            if (lane == 0) {
+                atomicAdd(&misc[kMValid], (uint32_t)nvalid);
+                if (bad) misc[kMBad] = 1u;
             }
         }
         group_bar(barid);
 
         // ---------------- P2: word prefix of the bitmap; occupied bins -> classes ---------------------------------
-        int d_total;
+        int d_total, npos;
         {
             const int w0 = gtid * a.wpt, w1 = min(w0 + a.wpt, n_words);
             uint32_t local = 0;
 #pragma unroll 1
             for (int w = w0; w < w1; ++w) local += __popc(A[w]);
-            static_assert(kTieNB / kTG == 8, "eight bins per thread");
-            const uint4 q0 = reinterpret_cast<const uint4*>(rep)[gtid * 2], q1 = reinterpret_cast<const uint4*>(rep)[gtid * 2 + 1];
-            const uint32_t occ = (q0.x ? 1u : 0u) | (q0.y ? 2u : 0u) | (q0.z ? 4u : 0u) | (q0.w ? 8u : 0u) |
-                                 (q1.x ? 16u : 0u) | (q1.y ? 32u : 0u) | (q1.z ? 64u : 0u) | (q1.w ? 128u : 0u);
+            constexpr int kBinsPT = kTieNB / kTG;         // bins per thread
+            static_assert(kBinsPT == 2 || kBinsPT == 4, "two or four bins per thread");
+            uint32_t occ;
+            if constexpr (kBinsPT == 4) {
+                const uint4 q0 = reinterpret_cast<const uint4*>(rep)[gtid];
+                occ = (q0.x ? 1u : 0u) | (q0.y ? 2u : 0u) | (q0.z ? 4u : 0u) | (q0.w ? 8u : 0u);
+            } else {
+                const uint2 q0 = reinterpret_cast<const uint2*>(rep)[gtid];
+                occ = (q0.x ? 1u : 0u) | (q0.y ? 2u : 0u);
+            }
+            // bin 0 also takes every value above the sampled range: it always belongs to the tail class (exact order)
+            if (gtid == 0) occ &= ~1u;
             uint32_t total;
-            const uint32_t excl = group_excl_scan((local << 16) | (uint32_t)__popc(occ), misc + 32, lane, gw, barid, total);
+            const uint32_t excl = group_excl_scan((local << 16) | (uint32_t)__popc(occ), misc + kMScanA, lane, gw, barid, total);
             d_total = (int)(total & 0xFFFFu);
-            const int n_bits = (int)(total >> 16);
+            npos = (int)(total >> 16);
             uint32_t run = excl >> 16;
 #pragma unroll 1
             for (int w = w0; w < w1; ++w) {
@@ -313,19 +414,20 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             // class of my bins: index among the occupied bins (descending value) minus the tail's share
             const int excess = max(0, d_total - (kTieD - 1));
             int code = (int)(excl & 0xFFFFu);
-            unsigned long long packed = 0ull;
+            uint32_t packed = 0u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if ((occ >> k) & 1u) {
-                    const int cls = code < excess ? 0 : code - excess + 1;
-                    packed |= (unsigned long long)cls << (8 * k);
-                    ++code;
-                }
+            for (int k = 0; k < kBinsPT; ++k) {
+                const int cls = code < excess ? 0 : code - excess + 1;
+                packed |= ((occ >> k) & 1u) ? (uint32_t)cls << (8 * k) : 0u;
+                code += (occ >> k) & 1u;
             }
-            reinterpret_cast<unsigned long long*>(code_of)[gtid] = packed;
+            if constexpr (kBinsPT == 4) reinterpret_cast<uint32_t*>(code_of)[gtid] = packed;
+            else reinterpret_cast<uint16_t*>(code_of)[gtid] = (uint16_t)packed;
+            const bool bad = misc[kMBad] != 0u;
+            const bool dup = (int)misc[kMValid] != npos;   // a column stored twice, or a column index out of range
             group_bar(barid);
-            if (n_bits != npos) {                          // a column stored twice, or a column index out of range
-                hand_over(cell, TIE_ST_DUP);
+            if (bad || dup) {
+                hand_over(cell, bad ? TIE_ST_BADVAL : TIE_ST_DUP);
                 continue;
             }
         }
@@ -333,87 +435,144 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         // ---------------- P3: entries into position order; class counts per chunk; the tail list ------------------
         const int ch = max(1, (npos + kTG - 1) / kTG);     // items per chunk (thread) in P6
         const uint32_t magic = ((1u << 20) + (uint32_t)ch - 1u) / (uint32_t)ch;
-#pragma unroll 4
-        for (int i = gtid; i < n; i += kTG) {
-            const uint32_t u = VT::bits(vals, i);
-            const unsigned col = (unsigned)cols[i];
-            if ((u << 1) != 0u) {
-                const unsigned pos = ip[col];
-                const unsigned w = pos >> 5;
-                const uint32_t j = (uint32_t)wpre[w] + (uint32_t)__popc(A[w] & ((1u << (pos & 31)) - 1u));
-                const uint32_t bin = (umax - u) >> shift;
-                const uint32_t cls = code_of[bin];
-                bpp[j] = (uint16_t)pos;
-                bpc[j] = (uint8_t)cls;
-                const uint32_t chunk = (j * magic) >> 20;
-                atomicAdd(&cnt32[(cls * kTG + chunk) >> 1], 1u << ((chunk & 1u) << 4));
-                if (cls == 0u) {
-                    const uint32_t f = atomicAdd(&misc[40], 1u);
-                    if (f < (uint32_t)kTieFix) fix[f] = make_uint2(u, pos);
-                } else if (rep[bin] != u) {
-                    misc[41] = 1u;                         // two different values in one class bin
+        {
+            uint32_t mixed = 0u;
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int base = it * (kTieU * kTG) + gtid;
+                uint32_t u[kTieU];
+                unsigned col[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool in = base + k * kTG < n;
+                    u[k] = in ? VT::bits(vals, base + k * kTG) : 0u;
+                    col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
+                }
+                bool any_tail = false;
+                uint32_t cls_k[kTieU], pos_k[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool valid = (u[k] << 1) != 0u;  // (columns are in range: P2 checked the bit count)
+                    const unsigned pos = ip[valid ? col[k] : 0u];
+                    const unsigned w = pos >> 5;
+                    const uint32_t jv = (uint32_t)wpre[w] + (uint32_t)__popc(A[w] & ((1u << (pos & 31)) - 1u));
+                    const uint32_t bin = bin_of(u[k]);
+                    const uint32_t cls = valid ? (uint32_t)code_of[bin] : 0u;
+                    const uint32_t j = valid ? jv : (uint32_t)cap;         // the spare slot behind the arrays
+                    bpp[j] = (uint16_t)pos;
+                    bpc[j] = (uint8_t)cls;
+                    const uint32_t chunk = valid ? ((jv * magic) >> 20) : 0u;
+                    atomicAdd(&cnt[cls * kTG + chunk], valid ? 1u : 0u);
+                    mixed |= (valid && cls != 0u && rep[bin] != u[k]) ? 1u : 0u;   // two values in one class bin
+                    any_tail |= valid && cls == 0u;
+                    cls_k[k] = valid ? cls : 1u;
+                    pos_k[k] = pos;
+                }
+                if (__any_sync(0xffffffffu, any_tail)) {   // rare: the largest values, beyond the kTieD - 1 classes
+#pragma unroll
+                    for (int k = 0; k < kTieU; ++k) {
+                        if (cls_k[k] == 0u) {
+                            const uint32_t f = atomicAdd(&misc[kMTail], 1u);
+                            if (f < (uint32_t)kTieFix) fix[f] = make_uint2(u[k], pos_k[k]);
+                        }
+                    }
                 }
             }
+            if (mixed) misc[kMMixed] = 1u;
         }
         group_bar(barid);
-        const int n_tail = (int)misc[40];
-        if (misc[41] != 0u || n_tail > kTieFix) {
-            hand_over(cell, misc[41] != 0u ? TIE_ST_MIXED : TIE_ST_TAIL);
+        const int n_tail = (int)misc[kMTail];
+        if (misc[kMMixed] != 0u || n_tail > kTieFix) {
+            const int why = misc[kMMixed] != 0u ? TIE_ST_MIXED : TIE_ST_TAIL;
             group_bar(barid);                              // the flags are cleared by the next cell: read them first
+            hand_over(cell, why);
             continue;
         }
 
         // ---------------- P5: exclusive scan of the counters in (class, chunk) order ------------------------------
         {
-            static_assert(kTieD * kTG / kTG == 32, "thread t scans the 32 counters [32 t, 32 t + 32) of class t / 4");
+            // thread t scans the kTieD counters [kTieD t, kTieD t + kTieD) of class kTieD t / kTG
+            constexpr int kVec = kTieD / 4;               // 128-bit vectors of counters per thread
+            static_assert(kTieD % 4 == 0 && kTG % kTieD == 0, "counter slices");
             const int n_cls = min(d_total, kTieD - 1) + 1;
-            const bool live = (gtid >> 2) < n_cls;
-            uint4 c[4];
+            const bool live = (gtid * kTieD) / kTG < n_cls;
+            uint4 c[kVec];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] = live ? reinterpret_cast<const uint4*>(cnt32)[gtid * 4 + k] : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < kVec; ++k) c[k] = live ? reinterpret_cast<const uint4*>(cnt)[gtid * kVec + k] : make_uint4(0u, 0u, 0u, 0u);
             uint32_t s = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s += c[k].x + c[k].y + c[k].z + c[k].w;       // both halves stay below 2^16
+            for (int k = 0; k < kVec; ++k) s += c[k].x + c[k].y + c[k].z + c[k].w;
             uint32_t total;
-            uint32_t run = group_excl_scan((s & 0xFFFFu) + (s >> 16), misc + 36, lane, gw, barid, total);
+            uint32_t run = group_excl_scan(s, misc + kMScanB, lane, gw, barid, total);
             if (live) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < kVec; ++k) {
                     uint32_t* const wv = reinterpret_cast<uint32_t*>(&c[k]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint32_t lo = wv[q] & 0xFFFFu, hi = wv[q] >> 16;
-                        wv[q] = run | ((run + lo) << 16);
-                        run += lo + hi;
+                        const uint32_t v = wv[q];
+                        wv[q] = run;
+                        run += v;
                     }
-                    reinterpret_cast<uint4*>(cnt32)[gtid * 4 + k] = c[k];
+                    reinterpret_cast<uint4*>(cnt)[gtid * kVec + k] = c[k];
                 }
             }
         }
         group_bar(barid);
 
         // ---------------- P6: rank in position order with private counters, scatter -------------------------------
+        // kTieP6 items per pass, the same number of passes for every thread of the group (threads past their chunk's
+        // end work on the spare slot with multiplier 0): ranks first -- the counters are private, so this is a short
+        // dependent chain --, then the table rows, then the atomics.  No branch per slot; the few rows that continue
+        // in a chain are put on the warp's list and applied afterwards.
         {
-            int j = gtid * ch;
-            const int j1 = min(j + ch, npos);
-            if (j < j1) {
-                unsigned pos_n = bpp[j], cc_n = bpc[j];
-                RowT row_n = tie_load_row<UNIT>(a, pos_n);
+            const int j0 = gtid * ch, j1 = min(j0 + ch, npos);
+            const int passes = (ch + kTieP6 - 1) / kTieP6;
 #pragma unroll 1
-                for (; j < j1; ++j) {
-                    const unsigned cc = cc_n;
-                    const RowT row = row_n;
-                    if (j + 1 < j1) {
-                        pos_n = bpp[j + 1];
-                        cc_n = bpc[j + 1];
-                        row_n = tie_load_row<UNIT>(a, pos_n);
-                    }
-                    uint16_t* const ctr = cnt16 + cc * kTG + gtid;
+            for (int it = 0; it < passes; ++it) {
+                const int j = j0 + it * kTieP6;
+                uint32_t m[kTieP6];
+                RowT row[kTieP6];
+#pragma unroll
+                for (int k = 0; k < kTieP6; ++k) {
+                    const bool in = j + k < j1;
+                    const int jj = in ? j + k : cap;
+                    const unsigned pos = bpp[jj];
+                    const unsigned cc = bpc[jj];
+                    uint32_t* const ctr = cnt + cc * kTG + gtid;
                     const int r = (int)*ctr;
-                    *ctr = (uint16_t)(r + 1);
-                    if (cc != 0u && r < cutoff) tie_apply<UNIT>(a, acc, row, (uint32_t)(cutoff - r), maskL);
+                    *ctr = (uint32_t)(r + 1);
+                    m[k] = (in && cc != 0u && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
+                    if (m[k]) row[k] = tie_load_row<UNIT>(a, pos);
+                }
+#pragma unroll
+                for (int k = 0; k < kTieP6; ++k) {
+                    if (m[k] == 0u) continue;               // not below the cutoff: nothing to add
+                    uint32_t start, cntc;
+                    const bool chain = tie_apply_direct<UNIT>(a, acc_s, row[k], m[k], maskL, dummy, start, cntc);
+                    if (chain) {
+                        const uint32_t at = atomicAdd(&misc[kMChain + gw], 1u);
+                        if (at < (uint32_t)kTieChainCap) {
+                            chain_list[at] = make_uint2(start, (cntc << 16) | m[k]);
+                        } else {                            // list full: apply it here
+                            if constexpr (UNIT) cntc = __ldg(a.xu + start);
+                            tie_apply_chain<UNIT>(a, acc_s, start, cntc, m[k], maskL);
+                        }
+                    }
                 }
             }
+            // the warp's deferred chains, one per lane
+            __syncwarp();
+            const int n_list = min((int)misc[kMChain + gw], kTieChainCap);
+#pragma unroll 1
+            for (int e = lane; e < n_list; e += 32) {
+                const uint2 ent = chain_list[e];
+                uint32_t cntc = ent.y >> 16;
+                if constexpr (UNIT) cntc = __ldg(a.xu + ent.x);
+                tie_apply_chain<UNIT>(a, acc_s, ent.x, cntc, ent.y & 0xFFFFu, maskL);
+            }
+            __syncwarp();
+            if (lane == 0) misc[kMChain + gw] = 0u;
         }
         // ---------------- P7: the tail (largest values): exact order by (value, position) -------------------------
 #pragma unroll 1
@@ -425,7 +584,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                 const uint2 o = fix[g];
                 r += (o.x > mine.x || (o.x == mine.x && o.y < mine.y)) ? 1 : 0;
             }
-            if (r < cutoff) tie_apply<UNIT>(a, acc, tie_load_row<UNIT>(a, mine.y), (uint32_t)(cutoff - r), maskL);
+            if (r < cutoff) tie_apply_full<UNIT>(a, acc_s, mine.y, (uint32_t)(cutoff - r), maskL, dummy);
         }
         // ---------------- P8: zeros fill the ranks npos .. cutoff-1 in position order ------------------------------
         const int q_zero = cutoff - npos;
@@ -438,7 +597,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                 const uint32_t bw = A[w];
                 if (!((bw >> (p & 31)) & 1u)) {
                     const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                    if (z < q_zero) tie_apply<UNIT>(a, acc, tie_load_row<UNIT>(a, (unsigned)p), (uint32_t)(q_zero - z), maskL);
+                    if (z < q_zero) tie_apply_full<UNIT>(a, acc_s, (unsigned)p, (uint32_t)(q_zero - z), maskL, dummy);
                 }
             }
         }
@@ -446,13 +605,31 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             if (a.out_nnz != nullptr) a.out_nnz[cell] = npos;
             if (a.stats != nullptr) atomicAdd(a.stats + TIE_ST_FAST, 1ull);
         }
-        group_bar(barid);
-
         // ---------------- P9: AUCs out, accumulators cleared -------------------------------------------------------
+        // the per-regulon constants do not depend on the accumulators: load them before the barrier
         double* const orow = a.out_auc + cell * (int64_t)R;
+        const int passes9 = (R + kTG - 1) / kTG;
+        int r9 = gtid;
+        int f_n = r9 < R ? __ldg(a.acc_first + r9) : -1;
+        int parts_n = 1;
+        double scale_n = 1.0, max_n = 1.0;
+        if (f_n >= 0) {
+            if constexpr (!UNIT) { parts_n = __ldg(a.acc_parts + r9); scale_n = __ldg(a.scale0 + r9); }
+            max_n = __ldg(a.max_auc + r9);
+        }
+        group_bar(barid);
 #pragma unroll 1
-        for (int r = gtid; r < R; r += kTG) {
-            const int f = __ldg(a.acc_first + r);
+        for (int it = 0; it < passes9; ++it, r9 += kTG) {
+            const int f = f_n, parts = parts_n;
+            const double scale = scale_n, mx = max_n;
+            if (it + 1 < passes9) {                        // next pass' constants while this one divides
+                const int rn = r9 + kTG;
+                f_n = rn < R ? __ldg(a.acc_first + rn) : -1;
+                if (f_n >= 0) {
+                    if constexpr (!UNIT) { parts_n = __ldg(a.acc_parts + rn); scale_n = __ldg(a.scale0 + rn); }
+                    max_n = __ldg(a.max_auc + rn);
+                }
+            }
             double res = 0.0;
             if (f >= 0) {
                 double sum;
@@ -460,21 +637,27 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                     sum = (double)acc[f];
                     acc[f] = 0u;
                 } else {
-                    const int parts = __ldg(a.acc_parts + r);
-                    sum = 0.0;
+                    uint2 lh = *reinterpret_cast<const uint2*>(acc + 2 * f);
+                    *reinterpret_cast<uint2*>(acc + 2 * f) = make_uint2(0u, 0u);
+                    if (f & 16) lh = make_uint2(lh.y, lh.x);              // low limb second (see tie_slot_w)
+                    sum = (double)(long long)(((unsigned long long)lh.y << a.L) + (unsigned long long)lh.x) * scale;
 #pragma unroll 1
-                    for (int k = 0; k < parts; ++k) {
-                        const uint2 lh = *reinterpret_cast<const uint2*>(acc + 2 * (f + k));
-                        const long long v = (long long)(((unsigned long long)lh.y << a.L) + (unsigned long long)lh.x);
-                        sum += (double)v * __ldg(a.acc_scale + f + k);
+                    for (int k = 1; k < parts; ++k) {                      // wide weight ranges: a second part
+                        uint2 l2 = *reinterpret_cast<const uint2*>(acc + 2 * (f + k));
                         *reinterpret_cast<uint2*>(acc + 2 * (f + k)) = make_uint2(0u, 0u);
+                        if ((f + k) & 16) l2 = make_uint2(l2.y, l2.x);
+                        const long long v = (long long)(((unsigned long long)l2.y << a.L) + (unsigned long long)l2.x);
+                        sum += (double)v * __ldg(a.acc_scale + f + k);
                     }
                 }
-                res = __ddiv_rn(sum, __ldg(a.max_auc + r));
+                // a zero numerator (no gene of the regulon below the cutoff: common) sends DDIV down its out-of-line
+                // special-case path for the whole warp: divide something harmless instead
+                const double q = __ddiv_rn(nonzero_numerator(sum), mx);
+                res = sum == 0.0 ? 0.0 : q;
             }
-            orow[r] = res;
+            if (r9 < R) orow[r9] = res;
         }
-        // no barrier: the next cell passes several group barriers before its first scatter
+        // no barrier: the next cell clears its working set and passes a group barrier before it touches anything else
     }
 }
 

@@ -14,7 +14,8 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_bounds_by_nnz", "gather_blocks", "global_column_max", "aucell_sharded"]
+__all__ = ["shard_bounds", "shard_bounds_by_nnz", "gather_blocks", "global_column_max", "aucell_sharded",
+           "aucell_csr_shard_from_host"]
 
 
 def shard_bounds(n_cells: int, world_size: int) -> List[Tuple[int, int]]:
@@ -85,3 +86,50 @@ def aucell_sharded(compute_shard: Callable[[int, int], "object"], n_cells: int, 
     if normalize:
         block = block / global_column_max(block, group)
     return gather_blocks(block, bounds, n_regulons, group=group, dst=dst)
+
+
+def aucell_csr_shard_from_host(plan, h_indptr, h_indices, h_data, bounds: Sequence[Tuple[int, int]], group=None,
+                               dst: int = 0, to_host: bool = True, timings: Optional[dict] = None):
+    """One rank's part of a cell-sharded AUCell job whose CSR matrix lives in HOST memory (the multi-GPU form of
+    ``pyscenic.aucell.aucell``, reference ``src/pyscenic/aucell.py:131-181``, which shares one ranking matrix between
+    forked workers; here cells are partitioned and only the result travels).
+
+    ``h_indptr`` / ``h_indices`` / ``h_data`` are torch CPU tensors (pinned for full PCIe rate) holding THIS rank's
+    cell range ``bounds[rank]``: ``h_indptr`` has ``c1 - c0 + 1`` entries (absolute or rebased offsets), the other two
+    the entries of those cells.  Upload, kernel, NCCL gather of the ``[cells x regulons]`` blocks to ``dst``, and (when
+    ``to_host``) the copy of the gathered matrix into pinned host memory there.  Returns the full matrix on ``dst``
+    (a pinned CPU tensor, or the CUDA tensor when ``to_host`` is false) and ``None`` on the other ranks.
+    ``timings`` (optional dict) receives the wall-clock seconds of the phases, measured around device synchronisations.
+    """
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", plan.device)
+    c0, c1 = bounds[rank]
+    assert h_indptr.numel() == c1 - c0 + 1
+    t0 = time.perf_counter()
+    d_ip = h_indptr.to(dev, non_blocking=True)
+    d_ix = h_indices.to(dev, non_blocking=True)
+    d_dv = h_data.to(dev, non_blocking=True)
+    d_ip = d_ip - d_ip[0]
+    block = plan.aucell_csr(d_ip, d_ix, d_dv)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    full = gather_blocks(block, bounds, plan.n_regulons, group=group, dst=dst)
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    res = None
+    if rank == dst:
+        if to_host:
+            res = torch.empty(full.shape, dtype=full.dtype, pin_memory=True)
+            res.copy_(full, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        else:
+            res = full
+    t3 = time.perf_counter()
+    if timings is not None:
+        timings.update(upload_and_kernel_s=t1 - t0, gather_s=t2 - t1, to_host_s=t3 - t2)
+    return res

@@ -6,7 +6,10 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "c
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None; items = []; tot_i = 0; tot_s = 0
+cur = "?"
 for r in rows:
+    if r and r[0] == "File Path":
+        cur = r[1].split("/")[-1]; continue
     if r and r[0] == "Line No":
         hdr = r; continue
     if hdr is None or len(r) < len(hdr) - 5: continue
@@ -15,8 +18,8 @@ for r in rows:
         n = int(r[hdr.index("Instructions Executed")]); s = int(r[hdr.index("# Samples")])
     except ValueError:
         continue
-    items.append((n, s, r[0], r[1].strip()[:100])); tot_i += n; tot_s += s
+    items.append((n, s, cur[:14] + ":" + r[0], r[1].strip()[:100])); tot_i += n; tot_s += s
 items.sort(reverse=True)
 print("total warp-instructions %d, samples %d" % (tot_i, tot_s))
 for n, s, l, src in items[:top]:
-    print("%12d %5.1f%%  stall-samples %5.1f%%  L%-4s %s" % (n, 100.0 * n / max(tot_i, 1), 100.0 * s / max(tot_s, 1), l, src))
+    print("%12d %5.1f%%  stall-samples %5.1f%%  %-20s %s" % (n, 100.0 * n / max(tot_i, 1), 100.0 * s / max(tot_s, 1), l, src))

@@ -1,0 +1,63 @@
+# -*- coding: utf-8 -*-
+"""One process per GPU (torchrun): partition ONE synthetic CSR matrix by stored entries, run every rank's shard from
+pinned host memory, gather the AUC blocks over NCCL to rank 0 and compare there, bit for bit, with the whole matrix
+computed on rank 0's GPU alone.  Prints one JSON line; used by tests/test_multigpu.py and by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/sharded_check.py --cells 60000
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import synth
+    from pyscenic_b200.plan import AUCellPlan, derive_rank_cutoff
+    from pyscenic_b200.sharding import aucell_csr_shard_from_host, shard_bounds_by_nnz
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, default=60000)
+    ap.add_argument("--genes", type=int, default=27998)
+    ap.add_argument("--regulons", type=int, default=500)
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rs = np.random.RandomState(1234)
+    reg = synth.make_regulons(rs, args.genes, args.regulons, 10, 400, weighted=True, repressors=True)
+    cutoff = derive_rank_cutoff(0.05, args.genes)
+    tables = synth.regulon_tables_from_arrays(*reg, n_genes=args.genes, rank_cutoff=cutoff)
+    perm = np.random.RandomState(42).permutation(args.genes)
+    plan = AUCellPlan(args.genes, perm, tables, device=local)
+    # the same matrix on every rank (seeded); a rank keeps only its shard on the host
+    indptr, indices, data = synth.synth_csr_torch(args.cells, args.genes, 1960, seed=77, device=dev)
+    bounds = shard_bounds_by_nnz(indptr.cpu().numpy(), world)
+    c0, c1 = bounds[rank]
+    e0, e1 = int(indptr[c0].item()), int(indptr[c1].item())
+    h_ip = indptr[c0:c1 + 1].cpu().pin_memory()
+    h_ix = indices[e0:e1].cpu().pin_memory()
+    h_dv = data[e0:e1].cpu().pin_memory()
+    timings = {}
+    full = aucell_csr_shard_from_host(plan, h_ip, h_ix, h_dv, bounds, timings=timings)
+    if rank == 0:
+        want = plan.aucell_csr(indptr, indices, data)
+        same = bool(torch.equal(full.to(dev), want))
+        print(json.dumps({"world": world, "cells": args.cells, "identical": same, "bounds": bounds, **timings}), flush=True)
+    dist.barrier()
+    plan.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -441,8 +441,9 @@ def test_config3_full_size_properties_and_spot_check():
         a = plan.aucell_csr(indptr, indices, data)
         b = plan.aucell_csr(indptr, indices, data)
         assert torch.equal(a, b)                                        # deterministic
-        stats = plan.path_stats()
-        assert stats["cells"] == 2 * n_cells
+        stats, fast = plan.path_stats(), plan.fast_stats()
+        assert stats["cells"] + fast["ranked"] == 2 * n_cells           # every cell ranked once, by one of the two kernels
+        assert fast["ranked"] > 1.9 * n_cells                             # count data: the tie-class kernel takes it
         # two halves computed separately == the whole (what cell sharding over GPUs relies on)
         mid = 41_337
         e_mid = int(indptr[mid])
@@ -489,11 +490,90 @@ def test_deep_cells_whose_selection_exceeds_the_register_capacity(n_genes):
     want = oracle_auc(X, perm, reg, cutoff)
     with _plan_for(n_genes, perm, reg, cutoff) as plan:
         got = plan.aucell_csr(indptr, indices, data).cpu().numpy()
-        stats = plan.path_stats()
+        stats, fast = plan.path_stats(), plan.fast_stats()
         got_d = plan.aucell_dense(torch.from_numpy(X).cuda()).cpu().numpy()
     assert_auc_close(got, want)
     assert np.array_equal(got, got_d)
-    assert stats["cells"] == n_cells
+    assert stats["cells"] + fast["ranked"] == n_cells
+
+
+def _mixed_bag_matrix(rs, n_genes):
+    """CSR rows that exercise every exit of the tie-class kernel: count-like rows (its home ground), an empty row, a row
+    with fewer entries than the cutoff (zero fill), explicit zeros, negatives, NaN, +inf, a continuous row, a row with
+    more distinct values than classes (tail), more than 128 tail values, two values in one bin, a row longer than the
+    kernel's capacity, a one-entry row."""
+    import scipy.sparse as sp
+
+    rows = []
+
+    def counts(n, lam=1.2):
+        v = np.zeros(n_genes, dtype=np.float32)
+        idx = rs.choice(n_genes, n, replace=False)
+        v[idx] = np.log1p(1 + np.floor(rs.exponential(lam, size=n))).astype(np.float32)
+        return v
+
+    for n in (1200, 300, 40, 2500, 1):
+        rows.append(counts(min(n, n_genes // 2)))
+    rows.append(np.zeros(n_genes, dtype=np.float32))                                     # empty
+    r = counts(800); r[rs.choice(n_genes, 30, replace=False)] = -2.5; rows.append(r)     # negatives
+    r = counts(800); r[rs.choice(n_genes, 5, replace=False)] = np.nan; rows.append(r)    # NaN
+    r = counts(800); r[rs.choice(n_genes, 3, replace=False)] = np.inf; rows.append(r)    # +inf
+    r = np.zeros(n_genes, dtype=np.float32); idx = rs.choice(n_genes, 900, replace=False)
+    r[idx] = rs.lognormal(0, 1, 900).astype(np.float32); rows.append(r)                  # continuous
+    r = np.zeros(n_genes, dtype=np.float32); idx = rs.choice(n_genes, 1500, replace=False)
+    r[idx] = (1 + np.floor(rs.exponential(12.0, 1500))).astype(np.float32); rows.append(r)   # ~60 distinct raw counts
+    r = np.zeros(n_genes, dtype=np.float32); idx = rs.choice(n_genes, 1500, replace=False)
+    r[idx] = (1 + np.floor(rs.exponential(200.0, 1500))).astype(np.float32); rows.append(r)  # hundreds of distinct values
+    r = counts(900); idx = np.flatnonzero(r)[:200]
+    r[idx[:100]] = np.float32(1.0); r[idx[100:]] = np.nextafter(np.float32(1.0), np.float32(2.0)); rows.append(r)  # one bin, two values
+    rows.append(counts(min(4600, n_genes - 10)))                                          # longer than the capacity
+    X = np.stack(rows)
+    m = sp.csr_matrix(X)
+    # explicit zeros in a count-like row (stored entries whose value is 0.0 / -0.0)
+    z = sp.csr_matrix(counts(700)[None, :])
+    z.data[::7] = 0.0
+    z.data[3::50] = -0.0
+    m = sp.vstack([m, z]).tocsr()
+    X = np.vstack([X, z.toarray()])
+    return X, m
+
+
+@pytest.mark.parametrize("unweighted", [False, True])
+@pytest.mark.parametrize("n_genes", [5000, 20011])
+def test_tie_class_kernel_equals_general_kernel_bit_for_bit(unweighted, n_genes):
+    """The two kernels behind aucell_csr_f32 / aucell_csr16_f32 add the same integers: switching the tie-class kernel
+    off must not change one bit, whatever mixture of cells the matrix holds; and both match the oracle."""
+    import torch
+
+    rs = np.random.RandomState(11)
+    X, m = _mixed_bag_matrix(rs, n_genes)
+    reps = 40                                            # enough cells for every cell group of every CTA
+    order = rs.permutation(np.tile(np.arange(X.shape[0]), reps))
+    m = m[order]
+    reg = synth.make_regulons(rs, n_genes, 120, 10, 400, weighted=not unweighted)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(3).permutation(n_genes)
+    indptr, indices, data = cuda(m.indptr.astype(np.int64)), cuda(m.indices.astype(np.int32)), cuda(m.data)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted=unweighted) as plan:
+        assert plan.set_fast_path(True)
+        nnz_f = torch.empty(m.shape[0], dtype=torch.int32, device="cuda")
+        fast = plan.aucell_csr(indptr, indices, data, out_nnz=nnz_f)
+        fs = plan.fast_stats()
+        fast16 = plan.aucell_csr(indptr, indices.to(torch.uint16), data)
+        plan.set_fast_path(False)
+        nnz_g = torch.empty_like(nnz_f)
+        general = plan.aucell_csr(indptr, indices, data, out_nnz=nnz_g)
+        plan.set_fast_path(True)
+    assert fs["ranked"] > 0 and fs["handed_long_row"] > 0 and fs["handed_negative_or_nan"] > 0
+    assert fs["handed_mixed_bin"] + fs["handed_tail_overflow"] + fs["handed_skipped"] > 0
+    assert fs["ranked"] + sum(v for k, v in fs.items() if k.startswith("handed")) == m.shape[0]
+    assert torch.equal(fast, general) and torch.equal(fast16, general)
+    assert torch.equal(nnz_f, nnz_g)
+    want = oracle_auc(X, perm, reg, cutoff, unweighted=unweighted)[order]
+    if unweighted:
+        assert np.array_equal(fast.cpu().numpy(), want)
+    else:
+        assert_auc_close(fast.cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.6, False), (0.6, True)])
