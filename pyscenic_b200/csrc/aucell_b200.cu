@@ -374,11 +374,21 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
         PCK(cudaMalloc(&p->d_acc_scale, sizeof(double) * nacc));
         PCK(cudaMemcpy(p->d_acc_scale, acc_scale.data(), sizeof(double) * nacc, cudaMemcpyHostToDevice));
         {
-            std::vector<double> scale0((size_t)n_regulons, 1.0);
-            for (int r = 0; r < n_regulons; ++r)
-                if (acc_first[r] >= 0) scale0[r] = acc_scale[(size_t)acc_first[r]];
-            PCK(cudaMalloc(&p->d_scale0, sizeof(double) * n_regulons));
-            PCK(cudaMemcpy(p->d_scale0, scale0.data(), sizeof(double) * n_regulons, cudaMemcpyHostToDevice));
+            struct Rec { double s0, s1, mx; int32_t first, has2; };
+            static_assert(sizeof(Rec) == 32, "epilogue record");
+            std::vector<Rec> recs((size_t)n_regulons);
+            for (int r = 0; r < n_regulons; ++r) {
+                Rec rc{0.0, 0.0, 1.0, -1, 0};
+                if (acc_first[r] >= 0) {
+                    rc.first = acc_first[r];
+                    rc.s0 = acc_scale[(size_t)acc_first[r]];
+                    rc.mx = h_reg_max_auc[r];
+                    if (acc_parts[r] > 1) { rc.has2 = 1; rc.s1 = acc_scale[(size_t)acc_first[r] + 1]; }
+                }
+                recs[(size_t)r] = rc;
+            }
+            PCK(cudaMalloc(&p->d_reg_rec, sizeof(Rec) * (size_t)n_regulons));
+            PCK(cudaMemcpy(p->d_reg_rec, recs.data(), sizeof(Rec) * (size_t)n_regulons, cudaMemcpyHostToDevice));
         }
         PCK(cudaMalloc(&p->d_reg_max_auc, sizeof(double) * n_regulons));
         PCK(cudaMemcpy(p->d_reg_max_auc, h_reg_max_auc, sizeof(double) * n_regulons, cudaMemcpyHostToDevice));
@@ -402,7 +412,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_ell_u);
     cudaFree(p->d_xu);
     cudaFree(p->d_tie_stats);
-    cudaFree(p->d_scale0);
+    cudaFree(p->d_reg_rec);
     cudaFree(p->d_acc_first);
     cudaFree(p->d_acc_parts);
     cudaFree(p->d_acc_scale);

@@ -104,7 +104,7 @@ struct aucell_plan {
     uint2* d_ell_u = nullptr;
     uint16_t* d_xu = nullptr;
     unsigned long long* d_tie_stats = nullptr;   // [TIE_ST_N]
-    double* d_scale0 = nullptr;                  // [R] acc_scale of every regulon's first accumulator
+    void* d_reg_rec = nullptr;                   // [R] 32-byte epilogue records of aucell_tie_kernel
     // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
     struct HostSlot {
         cudaStream_t st = nullptr;
@@ -235,7 +235,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     a.L = p->tie_L;
     a.n_regulons = p->n_regulons;
     a.acc_first = p->d_acc_first; a.acc_parts = p->d_acc_parts; a.acc_scale = p->d_acc_scale;
-    a.scale0 = p->d_scale0;
+    a.reg_rec = p->d_reg_rec;
     a.range = reinterpret_cast<const uint32_t*>(*todo_n) + 1;
     a.max_auc = p->d_reg_max_auc;
     a.out_auc = out_auc; a.out_nnz = out_nnz;

@@ -77,7 +77,8 @@ struct TieArgs {
     const int32_t* acc_first;           // [R] first accumulator of regulon r, -1 = invalid regulon
     const uint8_t* acc_parts;           // [R]
     const double* acc_scale;            // [n_acc]
-    const double* scale0;               // [R] acc_scale of the regulon's first accumulator
+    const void* reg_rec;                // [R] 32-byte records {double scale0, scale1 (0: none), max_auc; int32 first
+                                        //     accumulator (-1: invalid regulon), int32 has a second accumulator}
     const uint32_t* range;              // [2] bits of the smallest / largest positive value of a sample (tie_range_kernel)
     const double* max_auc;              // [R]
     double* out_auc;
@@ -159,18 +160,22 @@ __device__ __forceinline__ void tie_slot_u(uint32_t acc_s, uint32_t a, uint32_t 
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + (a << 2)), "r"(m) : "memory");
 }
 
-// the chained slots of a gene that sits in more than four regulons
+// The chained slots of genes that sit in more than four regulons, for a whole warp at once: every lane passes its own
+// chain (cnt = 0: none).  The trip count is the warp's maximum, so that the warp leaves the loop together -- lanes
+// leaving a loop one by one stay split for the rest of the cell (nothing downstream merges them again).
 template <bool UNIT>
-__device__ __forceinline__ void tie_apply_chain(const TieArgs& a, uint32_t acc_s, uint32_t start, uint32_t cnt,
-                                                uint32_t m, uint32_t maskL) {
-    if constexpr (UNIT) {
+__device__ __forceinline__ void tie_apply_chain_warp(const TieArgs& a, uint32_t acc_s, uint32_t start, uint32_t cnt,
+                                                     uint32_t m, uint32_t maskL) {
+    const uint32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
 #pragma unroll 1
-        for (uint32_t k = 1; k <= cnt; ++k) tie_slot_u(acc_s, __ldg(a.xu + start + k), m);
-    } else {
-#pragma unroll 1
-        for (uint32_t k = 0; k < cnt; ++k) {
-            const uint2 sl = __ldg(a.xw + start + k);
-            tie_slot_w(acc_s, sl.x, sl.y, m, a.L, maskL);
+    for (uint32_t k = 0; k < maxc; ++k) {
+        if (k < cnt) {
+            if constexpr (UNIT) {
+                tie_slot_u(acc_s, __ldg(a.xu + start + 1 + k), m);
+            } else {
+                const uint2 sl = __ldg(a.xw + start + k);
+                tie_slot_w(acc_s, sl.x, sl.y, m, a.L, maskL);
+            }
         }
     }
 }
@@ -200,16 +205,15 @@ __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_
     }
 }
 
-// whole row at once (the rare phases: tail, zero fill)
+// whole row at once, for a whole warp (tail, zero fill): lanes without work pass m = 0 and any valid position
 template <bool UNIT>
-__device__ __forceinline__ void tie_apply_full(const TieArgs& a, uint32_t acc_s, unsigned pos, uint32_t m,
-                                               uint32_t maskL, uint32_t dummy) {
+__device__ __forceinline__ void tie_apply_full_warp(const TieArgs& a, uint32_t acc_s, unsigned pos, uint32_t m,
+                                                    uint32_t maskL, uint32_t dummy) {
     const TieRow<UNIT> row = tie_load_row<UNIT>(a, pos);
     uint32_t start, cnt;
-    if (tie_apply_direct<UNIT>(a, acc_s, row, m, maskL, dummy, start, cnt)) {
-        if constexpr (UNIT) cnt = __ldg(a.xu + start);
-        tie_apply_chain<UNIT>(a, acc_s, start, cnt, m, maskL);
-    }
+    const bool chain = tie_apply_direct<UNIT>(a, acc_s, row, m, maskL, dummy, start, cnt);
+    if constexpr (UNIT) cnt = (chain && m != 0u) ? __ldg(a.xu + start) : 0u;
+    tie_apply_chain_warp<UNIT>(a, acc_s, start, (chain && m != 0u) ? cnt : 0u, m, maskL);
 }
 
 constexpr int kTieChainCap = kTieNB * 4 / (kTGW * 8);      // chained rows a warp can defer (the list reuses rep[])
@@ -554,9 +558,16 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                         const uint32_t at = atomicAdd(&misc[kMChain + gw], 1u);
                         if (at < (uint32_t)kTieChainCap) {
                             chain_list[at] = make_uint2(start, (cntc << 16) | m[k]);
-                        } else {                            // list full: apply it here
-                            if constexpr (UNIT) cntc = __ldg(a.xu + start);
-                            tie_apply_chain<UNIT>(a, acc_s, start, cntc, m[k], maskL);
+                        } else {                            // list full (never seen): apply it here, lane by lane
+                            if constexpr (UNIT) {
+                                cntc = __ldg(a.xu + start);
+                                for (uint32_t q = 1; q <= cntc; ++q) tie_slot_u(acc_s, __ldg(a.xu + start + q), m[k]);
+                            } else {
+                                for (uint32_t q = 0; q < cntc; ++q) {
+                                    const uint2 sl = __ldg(a.xw + start + q);
+                                    tie_slot_w(acc_s, sl.x, sl.y, m[k], a.L, maskL);
+                                }
+                            }
                         }
                     }
                 }
@@ -565,40 +576,42 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             __syncwarp();
             const int n_list = min((int)misc[kMChain + gw], kTieChainCap);
 #pragma unroll 1
-            for (int e = lane; e < n_list; e += 32) {
-                const uint2 ent = chain_list[e];
+            for (int base = 0; base < n_list; base += 32) {
+                const int e = base + lane;
+                const uint2 ent = e < n_list ? chain_list[e] : make_uint2(0u, 0u);
                 uint32_t cntc = ent.y >> 16;
-                if constexpr (UNIT) cntc = __ldg(a.xu + ent.x);
-                tie_apply_chain<UNIT>(a, acc_s, ent.x, cntc, ent.y & 0xFFFFu, maskL);
+                if constexpr (UNIT) cntc = e < n_list ? __ldg(a.xu + ent.x) : 0u;
+                tie_apply_chain_warp<UNIT>(a, acc_s, ent.x, cntc, ent.y & 0xFFFFu, maskL);
             }
             __syncwarp();
             if (lane == 0) misc[kMChain + gw] = 0u;
         }
         // ---------------- P7: the tail (largest values): exact order by (value, position) -------------------------
 #pragma unroll 1
-        for (int f = gtid; f < n_tail; f += kTG) {
-            const uint2 mine = fix[f];
+        for (int f0 = 0; f0 < n_tail; f0 += kTG) {         // (uniform trip counts: see tie_apply_chain_warp)
+            const int f = f0 + gtid;
+            const uint2 mine = f < n_tail ? fix[f] : make_uint2(0u, 0u);
             int r = 0;
 #pragma unroll 4
             for (int g = 0; g < n_tail; ++g) {
                 const uint2 o = fix[g];
                 r += (o.x > mine.x || (o.x == mine.x && o.y < mine.y)) ? 1 : 0;
             }
-            if (r < cutoff) tie_apply_full<UNIT>(a, acc_s, mine.y, (uint32_t)(cutoff - r), maskL, dummy);
+            const uint32_t m = (f < n_tail && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
+            tie_apply_full_warp<UNIT>(a, acc_s, mine.y, m, maskL, dummy);
         }
         // ---------------- P8: zeros fill the ranks npos .. cutoff-1 in position order ------------------------------
+        // the q_zero-th zero sits at a position below q_zero + npos = cutoff: every thread scans positions [0, cutoff)
         const int q_zero = cutoff - npos;
         if (q_zero > 0) {
 #pragma unroll 1
-            for (int p = gtid; p < n_genes; p += kTG) {
+            for (int p0 = 0; p0 < cutoff; p0 += kTG) {
+                const int p = min(p0 + gtid, n_genes - 1);
                 const int w = p >> 5;
-                const int z0 = (w << 5) - (int)wpre[w];
-                if (z0 >= q_zero) break;                   // words are visited in increasing order by every thread
                 const uint32_t bw = A[w];
-                if (!((bw >> (p & 31)) & 1u)) {
-                    const int z = z0 + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));
-                    if (z < q_zero) tie_apply_full<UNIT>(a, acc_s, (unsigned)p, (uint32_t)(q_zero - z), maskL, dummy);
-                }
+                const int z = (w << 5) - (int)wpre[w] + (p & 31) - __popc(bw & ((1u << (p & 31)) - 1u));   // zeros before p
+                const bool is_zero = p0 + gtid < cutoff && !((bw >> (p & 31)) & 1u) && z < q_zero;
+                tie_apply_full_warp<UNIT>(a, acc_s, (unsigned)p, is_zero ? (uint32_t)(q_zero - z) : 0u, maskL, dummy);
             }
         }
         if (gtid == 0) {
@@ -606,56 +619,52 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             if (a.stats != nullptr) atomicAdd(a.stats + TIE_ST_FAST, 1ull);
         }
         // ---------------- P9: AUCs out, accumulators cleared -------------------------------------------------------
-        // the per-regulon constants do not depend on the accumulators: load them before the barrier
+        // out[cell, r] = (double(acc) * 2^-s [+ double(acc') * 2^-s']) / max_auc[r].  Branch-free: a regulon without a
+        // second accumulator reads one of the dummies (always zero) with scale 0.  The per-regulon constants (one 32-byte
+        // record) do not depend on the accumulators: they are loaded before the barrier.  Same number of passes for
+        // every thread, and the warp is reconverged first (P7 / P8 leave it split).
+        __syncwarp();
         double* const orow = a.out_auc + cell * (int64_t)R;
         const int passes9 = (R + kTG - 1) / kTG;
         int r9 = gtid;
-        int f_n = r9 < R ? __ldg(a.acc_first + r9) : -1;
-        int parts_n = 1;
-        double scale_n = 1.0, max_n = 1.0;
-        if (f_n >= 0) {
-            if constexpr (!UNIT) { parts_n = __ldg(a.acc_parts + r9); scale_n = __ldg(a.scale0 + r9); }
-            max_n = __ldg(a.max_auc + r9);
-        }
+        const uint4* const recs = reinterpret_cast<const uint4*>(a.reg_rec);
+        const uint4 rec_none = make_uint4(0u, 0u, 0u, 0u), rec_none2 = make_uint4(0u, 0x3FF00000u, 0xFFFFFFFFu, 0u);
+        uint4 ra_n = r9 < R ? __ldg(recs + 2 * r9) : rec_none;             // s0, s1
+        uint4 rb_n = r9 < R ? __ldg(recs + 2 * r9 + 1) : rec_none2;        // max_auc, first accumulator (-1: none), has2
         group_bar(barid);
 #pragma unroll 1
         for (int it = 0; it < passes9; ++it, r9 += kTG) {
-            const int f = f_n, parts = parts_n;
-            const double scale = scale_n, mx = max_n;
+            const uint4 ra = ra_n, rb = rb_n;
             if (it + 1 < passes9) {                        // next pass' constants while this one divides
                 const int rn = r9 + kTG;
-                f_n = rn < R ? __ldg(a.acc_first + rn) : -1;
-                if (f_n >= 0) {
-                    if constexpr (!UNIT) { parts_n = __ldg(a.acc_parts + rn); scale_n = __ldg(a.scale0 + rn); }
-                    max_n = __ldg(a.max_auc + rn);
-                }
+                ra_n = rn < R ? __ldg(recs + 2 * rn) : rec_none;
+                rb_n = rn < R ? __ldg(recs + 2 * rn + 1) : rec_none2;
             }
-            double res = 0.0;
-            if (f >= 0) {
-                double sum;
-                if constexpr (UNIT) {
-                    sum = (double)acc[f];
-                    acc[f] = 0u;
-                } else {
-                    uint2 lh = *reinterpret_cast<const uint2*>(acc + 2 * f);
-                    *reinterpret_cast<uint2*>(acc + 2 * f) = make_uint2(0u, 0u);
-                    if (f & 16) lh = make_uint2(lh.y, lh.x);              // low limb second (see tie_slot_w)
-                    sum = (double)(long long)(((unsigned long long)lh.y << a.L) + (unsigned long long)lh.x) * scale;
-#pragma unroll 1
-                    for (int k = 1; k < parts; ++k) {                      // wide weight ranges: a second part
-                        uint2 l2 = *reinterpret_cast<const uint2*>(acc + 2 * (f + k));
-                        *reinterpret_cast<uint2*>(acc + 2 * (f + k)) = make_uint2(0u, 0u);
-                        if ((f + k) & 16) l2 = make_uint2(l2.y, l2.x);
-                        const long long v = (long long)(((unsigned long long)l2.y << a.L) + (unsigned long long)l2.x);
-                        sum += (double)v * __ldg(a.acc_scale + f + k);
-                    }
-                }
-                // a zero numerator (no gene of the regulon below the cutoff: common) sends DDIV down its out-of-line
-                // special-case path for the whole warp: divide something harmless instead
-                const double q = __ddiv_rn(nonzero_numerator(sum), mx);
-                res = sum == 0.0 ? 0.0 : q;
+            const int fx = (int)rb.z;
+            const int f = fx < 0 ? 0 : fx;                 // (invalid regulons read accumulator 0 and select 0.0 below)
+            const double mx = __hiloint2double((int)rb.y, (int)rb.x);
+            double sum;
+            if constexpr (UNIT) {
+                sum = (double)acc[f];
+                if (fx >= 0) acc[f] = 0u;
+            } else {
+                const bool has2 = rb.w != 0u;
+                const int f2 = has2 ? f + 1 : ((a.acc_words - 64) >> 1) + lane;
+                uint2 lh = *reinterpret_cast<const uint2*>(acc + 2 * f);
+                uint2 l2 = *reinterpret_cast<const uint2*>(acc + 2 * f2);
+                if (fx >= 0) *reinterpret_cast<uint2*>(acc + 2 * f) = make_uint2(0u, 0u);
+                if (has2) *reinterpret_cast<uint2*>(acc + 2 * f2) = make_uint2(0u, 0u);
+                if (f & 16) lh = make_uint2(lh.y, lh.x);                  // low limb second (see tie_slot_w)
+                if (f2 & 16) l2 = make_uint2(l2.y, l2.x);
+                const long long v0 = (long long)(((unsigned long long)lh.y << a.L) + (unsigned long long)lh.x);
+                const long long v1 = (long long)(((unsigned long long)l2.y << a.L) + (unsigned long long)l2.x);
+                sum = (double)v0 * __hiloint2double((int)ra.y, (int)ra.x);
+                sum += (double)v1 * __hiloint2double((int)ra.w, (int)ra.z);
             }
-            if (r9 < R) orow[r9] = res;
+            // a zero numerator (no gene of the regulon below the cutoff: common) would send DDIV down its out-of-line
+            // special-case path for the whole warp: divide something harmless instead
+            const double q = __ddiv_rn(nonzero_numerator(sum), mx);
+            if (r9 < R) orow[r9] = (sum == 0.0 || fx < 0) ? 0.0 : q;
         }
         // no barrier: the next cell clears its working set and passes a group barrier before it touches anything else
     }
