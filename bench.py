@@ -14,7 +14,12 @@ auc_threshold 0.05 (rank cutoff 1,399), seed 42.  Multi-GPU is weak scaling: eve
 shape (cells partition independently; no collective on the data path), `value` = all cells / max-over-ranks time.
 
 `e2e` is the same metric through the host-buffer C-ABI entry point (aucell_csr_f32_host): pinned HOST CSR in,
-pinned HOST AUC matrix out, H2D/D2H inside the timed region.
+pinned HOST AUC matrix out, H2D/D2H inside the timed region.  At N > 1 `e2e` is the STRONG-scaling job BASELINE.json's
+config 4 describes: ONE 1.3 M-cell matrix in host memory, partitioned over the ranks by stored entries
+(sharding.shard_bounds_by_nnz), every rank uploads and ranks its shard, the [cells x regulons] blocks are gathered over
+NCCL to rank 0 and copied to host memory there -- all inside the timed region -- and rank 0 then recomputes the whole
+matrix on its own GPU and checks the gathered result bit for bit (`sharded.identical`).  The weak-scaling host-buffer
+number of round 1 stays in the line as `e2e_weak`.
 
 `--impl reference` times the reference's CPU implementation of the path (oracle port: pandas create_rankings
 call-for-call + fork/RawArray regulon-chunk workers as in aucell.py:131-181 with the ctxcore AUC restated in C;
@@ -282,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
     launches = _native.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     path_stats = plan.path_stats()
+    fast_stats = plan.fast_stats()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,6 +342,58 @@ def run_ours(args, rank, world, local_rank):
         same = bool(torch.equal(h_out.to(dev), out[:n_e2e]))
         e2e["matches_device_path"] = same
 
+    # ---- strong scaling (N > 1): one matrix, cell-sharded, gathered over NCCL, verified ------------------------------
+    sharded = None
+    if world > 1 and w["kind"] == "csr" and not args.no_e2e:
+        from pyscenic_b200.sharding import aucell_csr_shard_from_host, scatter_csr_shards
+
+        n_tot = args.sharded_cells or n_cells
+        # host memory: every rank pins its shard (input / world) and rank 0 the result
+        need = (in_bytes / n_cells) * n_tot + 8.0 * R * n_tot
+        if need > 0.5 * mem_available_bytes():
+            n_tot = int(n_tot * 0.5 * mem_available_bytes() / need)
+        del out
+        # ONE matrix: rank 0's (torch's CUDA cumsum is not bit-reproducible from one device to the next, so the same
+        # seed does not give the same matrix on another GPU); the other ranks drop theirs and receive their shard
+        s_ip = s_ix = s_dv = None
+        if rank == 0:
+            if n_tot == n_cells:
+                s_ip, s_ix, s_dv = indptr, indices, data
+            else:
+                s_ip, s_ix, s_dv = synth.synth_csr_torch(n_tot, n_genes, w["mean_nnz"], seed=1000, device=dev)
+        else:
+            del indptr, indices, data
+            torch.cuda.empty_cache()
+        bounds, r_ip, r_ix, r_dv = scatter_csr_shards(s_ip, s_ix, s_dv)
+        h_ip, h_ix, h_dv = r_ip.cpu().pin_memory(), r_ix.cpu().pin_memory(), r_dv.cpu().pin_memory()
+        del r_ip, r_ix, r_dv
+        best = None
+        full = None
+        for it in range(3):                                   # first pass warms NCCL and the allocator; keep the best
+            tm = {}
+            barrier()
+            t0 = time.perf_counter()
+            full = aucell_csr_shard_from_host(plan, h_ip, h_ix, h_dv, bounds, timings=tm)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt, tm["upload_and_kernel_s"], tm["gather_s"], tm["to_host_s"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if it > 0 and (best is None or float(tt[0]) < best[0]):
+                best = [float(x) for x in tt]
+        if rank == 0:
+            want = plan.aucell_csr(s_ip, s_ix, s_dv)
+            identical = bool(torch.equal(full.to(dev), want))
+            total_in = int(s_ip.numel() * 8 + s_ix.numel() * 4 + s_dv.numel() * 4)
+            sharded = {"cells": int(n_tot), "seconds": best[0], "cells_per_s": n_tot / best[0],
+                       "upload_and_kernel_seconds": best[1], "gather_seconds": best[2], "to_host_seconds": best[3],
+                       "identical": identical, "partition": "contiguous cell ranges balanced by stored entries",
+                       "h2d_bytes": total_in, "d2h_bytes": int(n_tot) * R * 8,
+                       "timer": "host wall clock around upload + kernel + NCCL gather + copy to host, max over ranks, "
+                                "best of 2 after one warm-up pass"}
+            del want
+        launches += 3
+        out = None
+
     # ---- CPU baseline + parity check on a bounded sample (rank 0, N=1 only) ------------------------------------
     cpu_baseline = None
     parity = None
@@ -379,16 +437,25 @@ def run_ours(args, rank, world, local_rank):
                        "seed": SEED, "weighted": not args.unweighted,
                        "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9)},
             "clocks": clocks,
-            "e2e": e2e,
+            "e2e": e2e if sharded is None else {
+                "value": sharded["cells_per_s"], "unit": "cells/s", "h2d_bytes_per_step": sharded["h2d_bytes"],
+                "d2h_bytes_per_step": sharded["d2h_bytes"], "cells_per_step": sharded["cells"], "steps": 2,
+                "scaling": "strong: ONE matrix cell-sharded over the ranks, blocks gathered over NCCL to rank 0 and copied "
+                           "to host memory; checked bit for bit against a single-GPU run",
+                "timer": sharded["timer"]},
+            "e2e_weak": None if sharded is None else e2e,
+            "sharded": sharded,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "aucell_fused_kernel<%s>" % ("csr" if w["kind"] == "csr" else "dense"),
+                         "kernel": ("aucell_tie_kernel<csr> (cells it hands over: aucell_fused_kernel<csr>, same stream, inside "
+                                    "the timed region)" if w["kind"] == "csr" else "aucell_fused_kernel<dense>"),
                          "algorithmic_bytes_per_launch": int(alg_bytes),
                          "bytes_per_cell": alg_bytes / n_cells},
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "path_stats": path_stats,
+            "tie_kernel_stats": fast_stats,
         }
         print(json.dumps(line), flush=True)
     plan.close()
@@ -406,6 +473,7 @@ def main():
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (debugging)")
     ap.add_argument("--ref-cells", type=int, default=2048, help="cells in the CPU reference sample")
     ap.add_argument("--unweighted", action="store_true", help="unit gene weights (the CLI default of the reference)")
+    ap.add_argument("--sharded-cells", type=int, default=0, help="cells of the strong-scaling matrix at N > 1 (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

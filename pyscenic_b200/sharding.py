@@ -15,7 +15,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["shard_bounds", "shard_bounds_by_nnz", "gather_blocks", "global_column_max", "aucell_sharded",
-           "aucell_csr_shard_from_host"]
+           "aucell_csr_shard_from_host", "scatter_csr_shards"]
 
 
 def shard_bounds(n_cells: int, world_size: int) -> List[Tuple[int, int]]:
@@ -133,3 +133,44 @@ def aucell_csr_shard_from_host(plan, h_indptr, h_indices, h_data, bounds: Sequen
     if timings is not None:
         timings.update(upload_and_kernel_s=t1 - t0, gather_s=t2 - t1, to_host_s=t3 - t2)
     return res
+
+
+def scatter_csr_shards(indptr, indices, data, world_size: Optional[int] = None, group=None, src: int = 0):
+    """Distribute ONE CSR matrix that lives on ``src`` (torch tensors on its device; ``None`` on the other ranks): the
+    partition by stored entries is made on ``src`` and every rank receives its own cell range.  Returns
+    ``(bounds, indptr_shard, indices_shard, data_shard)`` -- tensors on the rank's current device (``nccl``) or on the
+    CPU (``gloo``), ``indptr_shard`` holding the absolute offsets of ``bounds[rank]``."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    world_size = world if world_size is None else world_size
+    meta = [None]
+    if rank == src:
+        ip = indptr.cpu().numpy()
+        bounds = shard_bounds_by_nnz(ip, world_size)
+        meta = [(bounds, [(int(ip[a]), int(ip[b])) for a, b in bounds], str(indices.dtype), str(data.dtype))]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    bounds, spans, ix_dt, dv_dt = meta[0]
+    if rank == src:
+        for r in range(world):
+            if r == src:
+                continue
+            (c0, c1), (e0, e1) = bounds[r], spans[r]
+            dist.send(indptr[c0:c1 + 1].contiguous(), dst=r, group=group)
+            if e1 > e0:
+                dist.send(indices[e0:e1].contiguous(), dst=r, group=group)
+                dist.send(data[e0:e1].contiguous(), dst=r, group=group)
+        (c0, c1), (e0, e1) = bounds[src], spans[src]
+        return bounds, indptr[c0:c1 + 1], indices[e0:e1], data[e0:e1]
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    (c0, c1), (e0, e1) = bounds[rank], spans[rank]
+    s_ip = torch.empty(c1 - c0 + 1, dtype=torch.int64, device=dev)
+    s_ix = torch.empty(e1 - e0, dtype=getattr(torch, ix_dt.split(".")[-1]), device=dev)
+    s_dv = torch.empty(e1 - e0, dtype=getattr(torch, dv_dt.split(".")[-1]), device=dev)
+    dist.recv(s_ip, src=src, group=group)
+    if e1 > e0:
+        dist.recv(s_ix, src=src, group=group)
+        dist.recv(s_dv, src=src, group=group)
+    return bounds, s_ip, s_ix, s_dv

@@ -22,7 +22,7 @@ def main():
 
     import synth
     from pyscenic_b200.plan import AUCellPlan, derive_rank_cutoff
-    from pyscenic_b200.sharding import aucell_csr_shard_from_host, shard_bounds_by_nnz
+    from pyscenic_b200.sharding import aucell_csr_shard_from_host, scatter_csr_shards
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=60000)
@@ -40,20 +40,28 @@ def main():
     tables = synth.regulon_tables_from_arrays(*reg, n_genes=args.genes, rank_cutoff=cutoff)
     perm = np.random.RandomState(42).permutation(args.genes)
     plan = AUCellPlan(args.genes, perm, tables, device=local)
-    # the same matrix on every rank (seeded); a rank keeps only its shard on the host
-    indptr, indices, data = synth.synth_csr_torch(args.cells, args.genes, 1960, seed=77, device=dev)
-    bounds = shard_bounds_by_nnz(indptr.cpu().numpy(), world)
-    c0, c1 = bounds[rank]
-    e0, e1 = int(indptr[c0].item()), int(indptr[c1].item())
-    h_ip = indptr[c0:c1 + 1].cpu().pin_memory()
-    h_ix = indices[e0:e1].cpu().pin_memory()
-    h_dv = data[e0:e1].cpu().pin_memory()
+    # ONE matrix, generated on rank 0 (torch's CUDA cumsum is not bit-reproducible from one device to the next, so
+    # "the same seed on every rank" does not give the same matrix); every rank receives its shard and keeps it in
+    # pinned host memory
+    indptr = indices = data = None
+    if rank == 0:
+        indptr, indices, data = synth.synth_csr_torch(args.cells, args.genes, 1960, seed=77, device=dev)
+    bounds, s_ip, s_ix, s_dv = scatter_csr_shards(indptr, indices, data)
+    h_ip, h_ix, h_dv = s_ip.cpu().pin_memory(), s_ix.cpu().pin_memory(), s_dv.cpu().pin_memory()
+    del s_ip, s_ix, s_dv
     timings = {}
     full = aucell_csr_shard_from_host(plan, h_ip, h_ix, h_dv, bounds, timings=timings)
     if rank == 0:
         want = plan.aucell_csr(indptr, indices, data)
-        same = bool(torch.equal(full.to(dev), want))
-        print(json.dumps({"world": world, "cells": args.cells, "identical": same, "bounds": bounds, **timings}), flush=True)
+        got = full.to(dev)
+        same = bool(torch.equal(got, want))
+        info = {}
+        if not same:
+            bad = (got != want).any(dim=1).nonzero().flatten()
+            info = {"bad_cells": int(bad.numel()), "first_bad": bad[:8].tolist(), "last_bad": bad[-8:].tolist(),
+                    "max_abs_diff": float((got - want).abs().max().item()),
+                    "again_equal": bool(torch.equal(plan.aucell_csr(indptr, indices, data), want))}
+        print(json.dumps({"world": world, "cells": args.cells, "identical": same, "bounds": bounds, **timings, **info}), flush=True)
     dist.barrier()
     plan.close()
     dist.destroy_process_group()

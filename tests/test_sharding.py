@@ -74,3 +74,50 @@ def test_gloo_world2_gather_matches_single_process(tmp_path, n_cells, normalize)
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, _free_port(), n_cells, 7, normalize, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def _scatter_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+
+    from pyscenic_b200.sharding import gather_blocks, scatter_csr_shards
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    indptr = indices = data = None
+    rs = np.random.RandomState(9)
+    nnz = rs.randint(0, 40, size=57).astype(np.int64)
+    ip = np.concatenate([[0], np.cumsum(nnz)])
+    ix = rs.randint(0, 1000, size=int(ip[-1])).astype(np.int32)
+    dv = rs.rand(int(ip[-1])).astype(np.float32)
+    if rank == 0:                                   # only the source holds the matrix
+        indptr, indices, data = torch.from_numpy(ip), torch.from_numpy(ix), torch.from_numpy(dv)
+    bounds, s_ip, s_ix, s_dv = scatter_csr_shards(indptr, indices, data)
+    c0, c1 = bounds[rank]
+    ok = (bounds == shard_bounds_by_nnz(ip, world)
+          and np.array_equal(s_ip.numpy(), ip[c0:c1 + 1])
+          and np.array_equal(s_ix.numpy(), ix[ip[c0]:ip[c1]]) and np.array_equal(s_dv.numpy(), dv[ip[c0]:ip[c1]]))
+    # a per-cell "kernel": the row sums; gathered blocks must reproduce the whole matrix' row sums in order
+    rel = (s_ip - s_ip[0]).numpy()
+    block = torch.tensor([[float(s_dv.numpy()[rel[i]:rel[i + 1]].astype(np.float64).sum())] for i in range(c1 - c0)],
+                         dtype=torch.float64).reshape(c1 - c0, 1)
+    full = gather_blocks(block, bounds, 1)
+    if rank == 0:
+        want = np.array([dv[ip[i]:ip[i + 1]].astype(np.float64).sum() for i in range(57)])
+        ok = ok and np.array_equal(full.numpy()[:, 0], want)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        open(out_path, "w").write("ok" if int(flag) == 1 else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_scatter_of_one_matrix_and_gather(tmp_path):
+    """The strong-scaling driver: ONE CSR matrix on rank 0, partitioned by stored entries, every rank receives its own
+    cell range (scatter_csr_shards), the per-rank blocks come back in order (gather_blocks)."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_scatter_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
