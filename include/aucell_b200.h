@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -117,6 +117,21 @@ int aucell_csr_f64(const aucell_plan_t* plan, const int64_t* d_indptr, const int
  * contract as aucell_csr_f32; it is what aucell_csr_f32_host uploads after narrowing the caller's int32 indices. */
 int aucell_csr16_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const uint16_t* d_indices,
                      const float* d_data, int64_t n_cells, double* d_out_auc, int32_t* d_out_nnz, void* stream);
+
+/* CSR with uint16 column indices and ONE-BYTE value codes: d_codes[e] indexes d_lut, a table of up to 256 float32 values
+ * (the distinct values of the matrix; counts and their normalisations have few).  3 instead of 8 bytes per stored entry:
+ * what aucell_csr_f32_host uploads while the matrix allows it.  d_vals_scratch (float, indexed like d_codes) receives
+ * the decoded values for the cells the tie-class kernel hands to the general kernel.  Same contract as aucell_csr_f32
+ * otherwise; output bit-identical to it on the decoded matrix. */
+int aucell_csr16_lut8_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const uint16_t* d_indices,
+                          const uint8_t* d_codes, const float* d_lut, float* d_vals_scratch, int64_t n_cells,
+                          double* d_out_auc, int32_t* d_out_nnz, void* stream);
+
+/* The same with int32 column indices: 5 bytes per stored entry (a host that prepares the upload only has to touch the
+ * values; any n_genes). */
+int aucell_csr_lut8_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                        const uint8_t* d_codes, const float* d_lut, float* d_vals_scratch, int64_t n_cells,
+                        double* d_out_auc, int32_t* d_out_nnz, void* stream);
 
 /* ---- aucell4r (aucell.py:98-182): AUCs from an existing uint32 ranking matrix [n_cells x n_genes]
  * (row_stride in elements).  The plan's regulon columns index the ranking matrix' columns directly (create the

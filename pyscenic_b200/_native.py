@@ -59,6 +59,8 @@ EXPORTED_SYMBOLS = [
     "aucell_plan_path_stats",
     "aucell_plan_last_host_bytes",
     "aucell_rss_f64",
+    "aucell_csr16_lut8_f32",
+    "aucell_csr_lut8_f32",
     "aucell_plan_set_fast_path",
     "aucell_plan_fast_stats",
 ]
@@ -226,6 +228,10 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         for name in ("aucell_csr_f32", "aucell_csr_f64", "aucell_csr16_f32"):
             f = getattr(lib, name)
             f.argtypes = [p, p, p, p, i64, p, p, p]
+            f.restype = c_int
+        for name in ("aucell_csr16_lut8_f32", "aucell_csr_lut8_f32"):
+            f = getattr(lib, name)
+            f.argtypes = [p, p, p, p, p, p, i64, p, p, p]
             f.restype = c_int
         lib.aucell_from_rankings_u32.argtypes = [p, p, i64, i64, p, p]
         lib.aucell_from_rankings_u32.restype = c_int

@@ -4,6 +4,7 @@
 #include "launch.cuh"
 
 #include <chrono>
+#include <memory>
 #include <thread>
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
@@ -40,6 +41,12 @@ DECL_CSR(double, f64)
 #undef DECL_CSR
 int fused_csr16_f32(const aucell_plan* p, const int64_t* indptr, const uint16_t* indices, const float* data,
                     int64_t n_cells, double* out_auc, int32_t* out_nnz, void* stream);
+int fused_csr16_lut8(const aucell_plan* p, const int64_t* indptr, const uint16_t* indices, const uint8_t* codes,
+                     const float* lut, float* scratch_vals, int64_t n_cells, double* out_auc, int32_t* out_nnz,
+                     void* stream);
+int fused_csr_lut8(const aucell_plan* p, const int64_t* indptr, const int32_t* indices, const uint8_t* codes,
+                   const float* lut, float* scratch_vals, int64_t n_cells, double* out_auc, int32_t* out_nnz,
+                   void* stream);
 }  // namespace aucell_host
 
 // ------------------------------------------------------------------------------------------------------
@@ -422,6 +429,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
         if (hs.st) { cudaStreamSynchronize(hs.st); cudaStreamDestroy(hs.st); }
         cudaFree(hs.buf);
         cudaFreeHost(hs.pin_idx);
+        cudaFreeHost(hs.pin_codes);
         if (hs.idx_done) cudaEventDestroy(hs.idx_done);
     }
     delete p;
@@ -508,6 +516,18 @@ int aucell_csr16_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const u
     return fused_csr16_f32(plan, d_indptr, d_indices, d_data, n_cells, d_out_auc, d_out_nnz, stream);
 }
 
+int aucell_csr16_lut8_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const uint16_t* d_indices,
+                          const uint8_t* d_codes, const float* d_lut, float* d_vals_scratch, int64_t n_cells,
+                          double* d_out_auc, int32_t* d_out_nnz, void* stream) {
+    return fused_csr16_lut8(plan, d_indptr, d_indices, d_codes, d_lut, d_vals_scratch, n_cells, d_out_auc, d_out_nnz, stream);
+}
+
+int aucell_csr_lut8_f32(const aucell_plan_t* plan, const int64_t* d_indptr, const int32_t* d_indices,
+                        const uint8_t* d_codes, const float* d_lut, float* d_vals_scratch, int64_t n_cells,
+                        double* d_out_auc, int32_t* d_out_nnz, void* stream) {
+    return fused_csr_lut8(plan, d_indptr, d_indices, d_codes, d_lut, d_vals_scratch, n_cells, d_out_auc, d_out_nnz, stream);
+}
+
 // ---- aucell4r ----------------------------------------------------------------------------------------
 int aucell_from_rankings_u32(const aucell_plan_t* p, const uint32_t* d_rank, int64_t n_cells, int64_t row_stride,
                              double* d_out_auc, void* stream) {
@@ -558,7 +578,7 @@ constexpr int kHostSlots = 4;
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Make sure the plan owns kHostSlots staging buffers of at least `bytes` each (and their streams).
-int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0) {
+int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0, size_t pin_codes_bytes = 0) {
     if (p->host_slots.empty()) p->host_slots.resize(kHostSlots);
     for (auto& hs : p->host_slots) {
         if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
@@ -578,7 +598,15 @@ int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes =
             CK(cudaHostAlloc((void**)&hs.pin_idx, pin_idx_bytes, cudaHostAllocDefault));
             hs.pin_bytes = pin_idx_bytes;
         }
-        if (pin_idx_bytes && !hs.idx_done) CK(cudaEventCreateWithFlags(&hs.idx_done, cudaEventDisableTiming));
+        if (hs.pin_codes_bytes < pin_codes_bytes) {
+            CK(cudaStreamSynchronize(hs.st));
+            cudaFreeHost(hs.pin_codes);
+            hs.pin_codes = nullptr;
+            hs.pin_codes_bytes = 0;
+            CK(cudaHostAlloc((void**)&hs.pin_codes, pin_codes_bytes, cudaHostAllocDefault));
+            hs.pin_codes_bytes = pin_codes_bytes;
+        }
+        if ((pin_idx_bytes || pin_codes_bytes) && !hs.idx_done) CK(cudaEventCreateWithFlags(&hs.idx_done, cudaEventDisableTiming));
         hs.idx_pending = false;
     }
     return AUCELL_OK;
@@ -647,6 +675,161 @@ bool narrow_indices(const int32_t* src, uint16_t* dst, int64_t n, int threads) {
     return any == 0;
 }
 
+// ---- one-byte value codes -----------------------------------------------------------------------------------------
+// Expression matrices hold few distinct values (raw counts, log1p / size-factor normalised counts): an append-only
+// dictionary of up to 256 float bit patterns turns the 4-byte values of the upload into 1-byte codes, losslessly
+// (the GPU reads the value bits back from the table).  Open addressing over 1024 slots; the values seen first -- the
+// frequent ones -- sit in their home slots, which is all the 8-wide AVX2 path probes.
+struct ValueDict {
+    static constexpr int kSlots = 1024, kMax = 256;
+    alignas(64) uint32_t key[kSlots];
+    alignas(64) uint32_t code[kSlots];      // 0xFFFFFFFF = empty
+    uint32_t lut[kMax];
+    int n = 0;
+    ValueDict() { clear(); }
+    void clear() {
+        n = 0;
+        for (int i = 0; i < kSlots; ++i) { key[i] = 0u; code[i] = 0xFFFFFFFFu; }
+        for (int i = 0; i < kMax; ++i) lut[i] = 0u;
+    }
+    static uint32_t home(uint32_t bits) { return (bits * 0x9E3779B1u) >> 22; }
+    int find(uint32_t bits) const {
+        for (uint32_t h = home(bits);; h = (h + 1) & (kSlots - 1)) {
+            if (code[h] == 0xFFFFFFFFu) return -1;
+            if (key[h] == bits) return (int)code[h];
+        }
+    }
+    bool insert(uint32_t bits) {            // false: full
+        if (find(bits) >= 0) return true;
+        if (n >= kMax) return false;
+        uint32_t h = home(bits);
+        while (code[h] != 0xFFFFFFFFu) h = (h + 1) & (kSlots - 1);
+        key[h] = bits;
+        code[h] = (uint32_t)n;
+        lut[n++] = bits;
+        return true;
+    }
+};
+
+// Encode src[0..n) into dst; stops at the first value that is not in the dictionary and returns its index (n: done).
+int64_t encode_span_scalar(const ValueDict& d, const uint32_t* src, uint8_t* dst, int64_t i, int64_t n) {
+    for (; i < n; ++i) {
+        const int c = d.find(src[i]);
+        if (c < 0) return i;
+        dst[i] = (uint8_t)c;
+    }
+    return n;
+}
+
+#ifdef AUCELL_HAVE_AVX2_PATH
+// Eight values per step.  The dictionary's first kTop values (the most frequent ones of the seed sample: a handful of
+// values make up > 99 % of a count matrix) are matched with compares against broadcast registers; a group holding any
+// other value goes through the table (gathers), and a value the table does not hold ends the span.  Codes are written
+// with streaming stores when `dst` is 32-byte aligned at a multiple of 32 values (the staging buffer is write-only).
+__attribute__((target("avx2"))) int64_t encode_span_avx2(const ValueDict& d, const uint32_t* src, uint8_t* dst, int64_t n) {
+    constexpr int kTop = 8;
+    __m256i top[kTop];
+    const int n_top = std::min(d.n, kTop);
+    for (int t = 0; t < kTop; ++t) top[t] = _mm256_set1_epi32((int)d.lut[t < n_top ? t : 0]);
+    const __m256i mul = _mm256_set1_epi32((int)0x9E3779B1u);
+    const __m256i ones = _mm256_set1_epi32(-1);
+    int64_t i = 0;
+    alignas(32) uint8_t line[32];
+    for (; i + 32 <= n; i += 32) {
+        bool miss = false;
+        for (int g = 0; g < 4 && !miss; ++g) {
+            const __m256i bits = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 8 * g));
+            __m256i c = _mm256_setzero_si256(), hit = _mm256_setzero_si256();
+            for (int t = 0; t < kTop; ++t) {                 // (t >= n_top repeats value 0 with code 0: harmless)
+                const __m256i eq = _mm256_cmpeq_epi32(bits, top[t]);
+                hit = _mm256_or_si256(hit, eq);
+                c = _mm256_or_si256(c, _mm256_and_si256(eq, _mm256_set1_epi32(t < n_top ? t : 0)));
+            }
+            if (_mm256_movemask_epi8(hit) != -1) {           // a rarer value among the eight: the table
+                const __m256i h = _mm256_srli_epi32(_mm256_mullo_epi32(bits, mul), 22);
+                const __m256i k = _mm256_i32gather_epi32(reinterpret_cast<const int*>(d.key), h, 4);
+                const __m256i cc = _mm256_i32gather_epi32(reinterpret_cast<const int*>(d.code), h, 4);
+                const __m256i ok = _mm256_or_si256(hit, _mm256_andnot_si256(_mm256_cmpeq_epi32(cc, ones), _mm256_cmpeq_epi32(k, bits)));
+                if (_mm256_movemask_epi8(ok) != -1) {        // displaced or unknown: one by one
+                    uint8_t tmp[8];
+                    const int64_t stop = encode_span_scalar(d, src + i + 8 * g, tmp, 0, 8);
+                    if (stop < 8) {                          // unknown value: flush what is done and stop there
+                        memcpy(dst + i, line, (size_t)(8 * g));
+                        memcpy(dst + i + 8 * g, tmp, (size_t)stop);
+                        return i + 8 * g + stop;
+                    }
+                    memcpy(line + 8 * g, tmp, 8);
+                    continue;
+                }
+                c = _mm256_blendv_epi8(cc, c, hit);
+            }
+            const __m256i p16 = _mm256_packus_epi32(c, c);
+            const __m256i p8 = _mm256_packus_epi16(p16, p16);
+            const uint32_t lo = (uint32_t)_mm256_extract_epi32(p8, 0), hi = (uint32_t)_mm256_extract_epi32(p8, 4);
+            const uint64_t both = (uint64_t)lo | ((uint64_t)hi << 32);
+            memcpy(line + 8 * g, &both, 8);
+        }
+        if ((reinterpret_cast<uintptr_t>(dst + i) & 31u) == 0)
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_load_si256(reinterpret_cast<const __m256i*>(line)));
+        else
+            memcpy(dst + i, line, 32);
+    }
+    _mm_sfence();
+    return encode_span_scalar(d, src, dst, i, n);
+}
+#endif
+
+int64_t encode_span(const ValueDict& d, const uint32_t* src, uint8_t* dst, int64_t n) {
+#ifdef AUCELL_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return encode_span_avx2(d, src, dst, n);
+#endif
+    return encode_span_scalar(d, src, dst, 0, n);
+}
+
+// Encode a chunk's values on `threads` host threads; values the dictionary does not know yet are added (by the calling
+// thread, between passes) while there is room.  Returns false when the chunk holds more than 256 distinct values.
+bool encode_values(ValueDict& d, const float* src_f, uint8_t* dst, int64_t n, int threads) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(src_f);
+    if (d.n == 0) {                         // seed: the distinct values of the first 64 k entries, most frequent first
+        std::map<uint32_t, int64_t> freq;
+        for (int64_t i = 0; i < std::min<int64_t>(n, 65536); ++i) {
+            ++freq[src[i]];
+            if (freq.size() > (size_t)ValueDict::kMax) return false;
+        }
+        std::vector<std::pair<int64_t, uint32_t>> by_count;
+        for (auto& kv : freq) by_count.push_back({-kv.second, kv.first});
+        std::sort(by_count.begin(), by_count.end());
+        for (auto& kv : by_count)
+            if (!d.insert(kv.second)) return false;
+    }
+    threads = std::max(1, n < (1 << 18) ? 1 : threads);
+    const int64_t per = ((n + threads - 1) / threads + 63) & ~int64_t(63);
+    std::vector<int64_t> pos((size_t)threads), end((size_t)threads);
+    for (int t = 0; t < threads; ++t) { pos[(size_t)t] = std::min(n, per * t); end[(size_t)t] = std::min(n, per * (t + 1)); }
+    for (;;) {
+        auto work = [&d, src, dst, &pos, &end](int t) {
+            const int64_t b = pos[(size_t)t], e = end[(size_t)t];
+            if (b < e) pos[(size_t)t] = b + encode_span(d, src + b, dst + b, e - b);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) {
+            if (pos[(size_t)t] >= end[(size_t)t]) continue;
+            try { pool.emplace_back(work, t); } catch (...) { work(t); }
+        }
+        work(0);
+        for (auto& th : pool) th.join();
+        bool done = true;
+        for (int t = 0; t < threads; ++t) {
+            if (pos[(size_t)t] < end[(size_t)t]) {          // stopped at an unknown value: learn it, go on from there
+                done = false;
+                if (!d.insert(src[pos[(size_t)t]])) return false;
+            }
+        }
+        if (done) return true;
+    }
+}
+
 int host_threads() {
     const char* env = getenv("AUCELL_B200_HOST_THREADS");
     if (env && *env) return std::max(1, std::min(64, atoi(env)));
@@ -688,22 +871,36 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     const size_t o_indptr = 0;
     const size_t o_indices = align256(o_indptr + sizeof(int64_t) * (chunk_cells + 1));
     const size_t o_vals = align256(o_indices + sizeof(int32_t) * std::max<int64_t>(max_nnz, 1));
-    const size_t o_auc = align256(o_vals + sizeof(float) * std::max<int64_t>(max_nnz, 1));
+    const size_t o_codes = align256(o_vals + sizeof(float) * std::max<int64_t>(max_nnz, 1));
+    const size_t o_lut = align256(o_codes + std::max<int64_t>(max_nnz, 1));
+    const size_t o_auc = align256(o_lut + sizeof(uint32_t) * ValueDict::kMax);
     const size_t o_nnz = align256(o_auc + sizeof(double) * chunk_cells * R);
     const size_t bytes = align256(o_nnz + sizeof(int32_t) * chunk_cells);
-    // 16-bit positions: upload the column indices as uint16 (a quarter less PCIe traffic; the link is the bottleneck
-    // of this call).  AUCELL_B200_HOST_IDX16=0 keeps the int32 upload.
+    // The link is the bottleneck of this call, so it sends less than the caller's arrays hold:
+    //  - 16-bit positions: the column indices go up as uint16 (AUCELL_B200_HOST_IDX16=0 keeps int32);
+    //  - the values go up as one-byte codes into a table of the distinct values (AUCELL_B200_HOST_VAL8=0 keeps float32),
+    //    while the matrix holds at most 256 of them (counts and their normalisations do).
+    // 3 instead of 8 bytes per stored entry; both narrowings run on host threads, chunk by chunk, ahead of the uploads.
     const char* env16 = getenv("AUCELL_B200_HOST_IDX16");
-    bool idx16 = p->pos16 && max_nnz > 0 && !(env16 && env16[0] == '0');
+    const char* env8 = getenv("AUCELL_B200_HOST_VAL8");
+    const bool idx16_allowed = p->pos16 && max_nnz > 0 && !(env16 && env16[0] == '0');
     const bool idx16_forced = env16 && env16[0] == '1';
+    const bool val8_allowed = max_nnz > 0 && p->fast_ok && !(env8 && env8[0] == '0');
+    const bool val8_forced = env8 && env8[0] == '1';
+    // start from the format the previous call on this plan settled on (same host, same kind of matrix)
+    bool idx16 = idx16_allowed && (p->hint_idx16 || idx16_forced);
+    bool val8 = val8_allowed && (p->hint_val8 || val8_forced);
+    std::unique_ptr<ValueDict> dict(val8 ? new (std::nothrow) ValueDict() : nullptr);
+    if (val8 && !dict) val8 = false;
     double narrow_ns = 0.0;               // time spent narrowing and entries narrowed so far in this call
     int64_t narrow_n = 0;
     int narrow_chunks = 0;
     int chunk_no = 0;                     // pipeline rate once the slots are full: entries enqueued per second
     int64_t rate_n = 0;
     std::chrono::steady_clock::time_point rate_t0;
-    const int n_threads = idx16 ? host_threads() : 1;
-    int rc = ensure_host_slots(p, bytes, idx16 ? sizeof(uint16_t) * (size_t)max_nnz : 0);
+    const int n_threads = (idx16 || val8) ? host_threads() : 1;
+    int rc = ensure_host_slots(p, bytes, idx16_allowed ? sizeof(uint16_t) * (size_t)max_nnz : 0,
+                               val8 ? (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax : 0);
     if (rc) return rc;
     int k = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -712,53 +909,96 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         int64_t* d_indptr = reinterpret_cast<int64_t*>(s.buf + o_indptr);
         int32_t* d_indices = reinterpret_cast<int32_t*>(s.buf + o_indices);
         float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
+        uint8_t* d_codes = reinterpret_cast<uint8_t*>(s.buf + o_codes);
+        float* d_lut = reinterpret_cast<float*>(s.buf + o_lut);
         double* d_auc = reinterpret_cast<double*>(s.buf + o_auc);
         int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
         const int64_t c1 = std::min(n_cells, c0 + chunk_cells);
         const int64_t nc = c1 - c0;
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
+        bool chunk8 = false;
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
         CKB(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
-        h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1) + ne * (int64_t)(sizeof(float) + (idx16 ? 2 : 4));
+        h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1);
         d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         if (ne > 0) {
-            if (idx16) {
-                if (s.idx_pending) CKB(cudaEventSynchronize(s.idx_done));      // staging buffer free again
+            const bool staged = idx16 || val8;
+            if (staged) {
+                if (s.idx_pending) CKB(cudaEventSynchronize(s.idx_done));      // staging buffers free again
                 s.idx_pending = false;
-                const auto t0 = std::chrono::steady_clock::now();
-                if (!narrow_indices(h_indices + e0, s.pin_idx, ne, n_threads)) {
-                    rc = fail(AUCELL_ERR_INVALID, "CSR column index out of range");
-                    break;
-                }
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            if (idx16 && !narrow_indices(h_indices + e0, s.pin_idx, ne, n_threads)) {
+                rc = fail(AUCELL_ERR_INVALID, "CSR column index out of range");
+                break;
+            }
+            if (val8) {
+                chunk8 = encode_values(*dict, h_data + e0, s.pin_codes, ne, n_threads);
+                if (!chunk8) val8 = false;                                     // more than 256 distinct values: float32 from here on
+            }
+            if (staged) {
                 narrow_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
                 narrow_n += ne;
                 ++narrow_chunks;
+            }
+            if (idx16) {
                 CKB(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, s.st));
-                CKB(cudaEventRecord(s.idx_done, s.st));
-                s.idx_pending = true;
+                h2d_bytes += (int64_t)sizeof(uint16_t) * ne;
             } else {
                 CKB(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+                h2d_bytes += (int64_t)sizeof(int32_t) * ne;
             }
-            CKB(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
+            if (chunk8) {
+                uint32_t* const pin_lut = reinterpret_cast<uint32_t*>(s.pin_codes + max_nnz);
+                memcpy(pin_lut, dict->lut, sizeof(uint32_t) * ValueDict::kMax);
+                CKB(cudaMemcpyAsync(d_codes, s.pin_codes, (size_t)ne, cudaMemcpyHostToDevice, s.st));
+                CKB(cudaMemcpyAsync(d_lut, pin_lut, sizeof(uint32_t) * ValueDict::kMax, cudaMemcpyHostToDevice, s.st));
+                h2d_bytes += ne + (int64_t)sizeof(uint32_t) * ValueDict::kMax;
+            } else {
+                CKB(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
+                h2d_bytes += (int64_t)sizeof(float) * ne;
+            }
+            if (staged) {
+                CKB(cudaEventRecord(s.idx_done, s.st));
+                s.idx_pending = true;
+            }
         }
         // the kernel indexes indices/data with the absolute offsets of h_indptr: shift the bases
-        if (idx16)
+        const bool chunk16 = idx16 && ne > 0;
+        if (chunk8 && chunk16)
+            rc = aucell_csr16_lut8_f32(p, d_indptr, reinterpret_cast<uint16_t*>(d_indices) - e0, d_codes - e0, d_lut,
+                                       d_vals - e0, nc, d_auc, d_nnz, s.st);
+        else if (chunk8)
+            rc = aucell_csr_lut8_f32(p, d_indptr, d_indices - e0, d_codes - e0, d_lut, d_vals - e0, nc, d_auc, d_nnz, s.st);
+        else if (chunk16)
             rc = aucell_csr16_f32(p, d_indptr, reinterpret_cast<uint16_t*>(d_indices) - e0, d_vals - e0, nc, d_auc,
                                   d_nnz, s.st);
         else
             rc = aucell_csr_f32(p, d_indptr, d_indices - e0, d_vals - e0, nc, d_auc, d_nnz, s.st);
         if (rc) break;
-        // a host that narrows slower than the link moves the int32 indices it saves (busy or few cores) is better off
-        // with the plain upload: ~6.5 G entries/s is what the 8-byte-per-entry path sustains on PCIe 5 x16
-        if (idx16 && !idx16_forced && narrow_chunks == 3 && narrow_n > (1 << 22) && narrow_ns > (double)narrow_n / 6.5)
-            idx16 = false;
+        // Preparing a chunk only pays while the host does it faster than the link would carry the next plainer format
+        // (PCIe 5 x16 sustains ~50 GB/s: 0.10 ns per entry at 5 bytes, 0.12 at 6, 0.154 at 8).  Measured over three
+        // chunks per format, the call steps down: both narrowings (3 bytes per entry, the host touches 11) -> byte codes
+        // only (5, touches 5: the indices go up by DMA as they are) -> uint16 indices only (6, touches 6) -> as is (8).
+        if (narrow_chunks == 3 && narrow_n > (1 << 22)) {
+            const double t = narrow_ns / (double)narrow_n;
+            bool changed = false;
+            if (val8 && idx16) {
+                if (t > 0.10 && !idx16_forced) { idx16 = false; changed = true; }
+            } else if (val8) {
+                if (t > 0.12 && !val8_forced) { val8 = false; idx16 = idx16_allowed; changed = true; }
+            } else if (idx16) {
+                if (t > 0.154 && !idx16_forced) { idx16 = false; changed = true; }
+            }
+            if (changed) { narrow_ns = 0.0; narrow_n = 0; narrow_chunks = 0; }
+        }
         // ... and when the pipeline as a whole runs well below what the link carries (several GPUs behind one host
         // memory system: measured 8 ranks on 32 cores), narrowing only adds host memory traffic: stop it.  The enqueue
         // loop is throttled by the slots, so its period is the pipeline's.
         ++chunk_no;
         if (chunk_no == kHostSlots) rate_t0 = std::chrono::steady_clock::now();
         if (chunk_no > kHostSlots) rate_n += ne;
-        if (idx16 && !idx16_forced && chunk_no == 3 * kHostSlots && rate_n > (1 << 24)) {
+        if (idx16 && !idx16_forced && !val8 && chunk_no == 3 * kHostSlots && rate_n > (1 << 24)) {
             const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - rate_t0).count();
             if (ns > (double)rate_n / 4.5) idx16 = false;        // < 4.5 G entries/s
         }
@@ -771,6 +1011,15 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     }
     p->last_h2d_bytes = h2d_bytes;
     p->last_d2h_bytes = d2h_bytes;
+    if (rc == AUCELL_OK && total_nnz > (1 << 24)) {       // (a small call measures nothing)
+        p->hint_idx16 = idx16 || !idx16_allowed;
+        p->hint_val8 = val8 || !val8_allowed;
+    }
+    if (const char* dbg = getenv("AUCELL_B200_DEBUG"); dbg && dbg[0] == '1')
+        fprintf(stderr, "[aucell_b200] csr host call: %lld cells, %lld entries, host prep %.3f s (%.2f G entries/s, %d threads), "
+                        "idx16 %d val8 %d, h2d %.2f GB d2h %.2f GB\n", (long long)n_cells, (long long)total_nnz, narrow_ns * 1e-9,
+                narrow_ns > 0 ? (double)narrow_n / narrow_ns : 0.0, n_threads, (int)idx16, (int)val8, h2d_bytes * 1e-9,
+                d2h_bytes * 1e-9);
     return rc;
 }
 

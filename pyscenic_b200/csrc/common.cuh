@@ -9,7 +9,8 @@ namespace aucell {
 
 // IN_CSR16: CSR with uint16 column indices (n_genes <= 65535): 6 instead of 8 bytes per stored entry over PCIe / HBM
 // IN_CSR16_U8: uint16 column indices and uint8 values (integer counts <= 255): 3 bytes per stored entry
-enum InputKind { IN_DENSE = 0, IN_CSR = 1, IN_CSR16 = 2, IN_CSR16_U8 = 3 };
+// IN_CSR_U8: int32 column indices and uint8 values: 5 bytes per stored entry (the host only has to touch the values)
+enum InputKind { IN_DENSE = 0, IN_CSR = 1, IN_CSR16 = 2, IN_CSR16_U8 = 3, IN_CSR_U8 = 4 };
 
 template <int IN> struct IdxOf { using type = int32_t; };
 template <> struct IdxOf<IN_CSR16> { using type = uint16_t; };

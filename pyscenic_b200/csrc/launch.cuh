@@ -112,11 +112,14 @@ struct aucell_plan {
         size_t bytes = 0;
         uint16_t* pin_idx = nullptr;   // pinned host staging of a chunk's column indices narrowed to uint16
         size_t pin_bytes = 0;
+        uint8_t* pin_codes = nullptr;  // pinned host staging of a chunk's values as one-byte codes, then the 1 KB table
+        size_t pin_codes_bytes = 0;
         cudaEvent_t idx_done = nullptr;   // the upload out of pin_idx has finished
         bool idx_pending = false;
     };
     mutable std::mutex host_mu;
     mutable int64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // what the last host-buffer call moved over PCIe
+    mutable bool hint_idx16 = true, hint_val8 = true;         // upload format the last host-buffer call settled on
     mutable std::vector<HostSlot> host_slots;
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;
@@ -216,7 +219,8 @@ inline int tie_cap() {
 // Launch aucell_tie_kernel over all cells; cells it leaves are listed in *todo (count in **todo_n, device memory).
 template <int IN>
 int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices, const void* data, int64_t n_cells,
-               double* out_auc, int32_t* out_nnz, cudaStream_t st, int32_t** todo, int32_t** todo_n, bool* launched) {
+               double* out_auc, int32_t* out_nnz, cudaStream_t st, int32_t** todo, int32_t** todo_n, bool* launched,
+               const uint32_t* lut = nullptr) {
     *launched = false;
     TieArgs a;
     memset(&a, 0, sizeof a);
@@ -226,7 +230,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     int rc = get_todo(p, st, n_cells, todo, todo_n);
     if (rc) return rc;
     CK(cudaMemsetAsync(*todo_n, 0, sizeof(int32_t), st));
-    a.indptr = indptr; a.indices = indices; a.data = data;
+    a.indptr = indptr; a.indices = indices; a.data = data; a.lut = lut;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
     a.wpt = (p->n_words + kTG - 1) / kTG;
     a.cutoff = (int)p->rank_cutoff;
@@ -242,7 +246,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     a.todo = *todo; a.todo_n = *todo_n;
     a.stats = p->d_tie_stats;
     const int grid = (int)std::min<int64_t>(p->sm_count, (n_cells + L.groups - 1) / L.groups);
-    tie_range_kernel<IN><<<1, 1024, 0, st>>>(indptr, n_cells, data, reinterpret_cast<uint32_t*>(*todo_n) + 1);
+    tie_range_kernel<IN><<<1, 1024, 0, st>>>(indptr, n_cells, data, lut, reinterpret_cast<uint32_t*>(*todo_n) + 1);
     launch_counter().fetch_add(1);
 #define LAUNCH_TIE(UNIT)                                                                          \
     do {                                                                                          \
@@ -287,10 +291,12 @@ int launch_fused(const aucell_plan* p, FusedArgs<ValT>& a, int smem, int64_t n_c
     return AUCELL_OK;
 }
 
+// pre_todo / pre_todo_n: a to-do list some other launch has already prepared on this stream (the byte-coded entry point:
+// its tie-class kernel reads codes, this kernel the decoded values); the tie-class kernel is then not launched here.
 template <typename ValT, int IN>
 int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const int64_t* indptr,
               const int32_t* indices, const ValT* data, int64_t n_cells, double* out_auc, int32_t* out_nnz,
-              void* stream) {
+              void* stream, int32_t* pre_todo = nullptr, int32_t* pre_todo_n = nullptr, bool allow_tie = true) {
     if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
     if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
     if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
@@ -340,8 +346,11 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
     a.scratch_cap = next_pow2(p->n_genes);
     // Count-like cells go through the tie-class kernel; what it leaves (long rows, negative / NaN values, continuous
     // values) comes back as a to-do list for the kernel below.
-    if constexpr (IN != IN_DENSE && std::is_same<ValT, float>::value) {
-        if (p->fast_ok && p->fast_enabled && n_cells < (int64_t)INT32_MAX) {
+    if (pre_todo != nullptr) {
+        a.todo = pre_todo;
+        a.todo_n = pre_todo_n;
+    } else if constexpr (IN != IN_DENSE && std::is_same<ValT, float>::value) {
+        if (allow_tie && p->fast_ok && p->fast_enabled && n_cells < (int64_t)INT32_MAX) {
             bool launched = false;
             int32_t *todo = nullptr, *todo_n = nullptr;
             int rc = launch_tie<IN>(p, indptr, indices, data, n_cells, out_auc, out_nnz, st, &todo, &todo_n, &launched);
@@ -355,6 +364,37 @@ int run_fused(const aucell_plan* p, const ValT* dense, int64_t row_stride, const
         if (p->pos16) return launch_fused<ValT, uint16_t, IN>(p, a, smem, n_cells, st, key_bytes);
         return launch_fused<ValT, uint32_t, IN>(p, a, smem, n_cells, st, key_bytes);
     }
+}
+
+// CSR with one-byte value codes (a table of up to 256 float values) and uint16 (IN_TIE = IN_CSR16_U8) or int32
+// (IN_CSR_U8) column indices: the tie-class kernel reads the codes; the values are decoded into `scratch_vals` (indexed
+// like the codes) for the cells it hands over.
+template <int IN_TIE>
+int run_fused_lut8(const aucell_plan* p, const int64_t* indptr, const void* indices, const uint8_t* codes,
+                   const float* lut, float* scratch_vals, int64_t n_cells, double* out_auc, int32_t* out_nnz,
+                   void* stream) {
+    constexpr int IN_GEN = IN_TIE == IN_CSR16_U8 ? IN_CSR16 : IN_CSR;
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
+    if (n_cells == 0) return AUCELL_OK;
+    if (!indptr || !lut || !scratch_vals || !out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    if (IN_TIE == IN_CSR16_U8 && !p->pos16) return fail(AUCELL_ERR_INVALID, "uint16 column indices need n_genes <= 65535");
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *todo = nullptr, *todo_n = nullptr;
+    bool launched = false;
+    if (p->fast_ok && p->fast_enabled && n_cells < (int64_t)INT32_MAX && p->rank_cutoff <= p->n_genes) {
+        int rc = launch_tie<IN_TIE>(p, indptr, indices, codes, n_cells, out_auc, out_nnz, st, &todo, &todo_n, &launched,
+                                    reinterpret_cast<const uint32_t*>(lut));
+        if (rc) return rc;
+    }
+    tie_decode_kernel<IN_TIE><<<p->sm_count * 8, 256, 0, st>>>(codes, reinterpret_cast<const uint32_t*>(lut), scratch_vals, indptr, n_cells);
+    launch_counter().fetch_add(1);
+    CK(cudaGetLastError());
+    return run_fused<float, IN_GEN>(p, nullptr, 0, indptr, reinterpret_cast<const int32_t*>(indices), scratch_vals, n_cells,
+                                    out_auc, out_nnz, stream, launched ? todo : nullptr, launched ? todo_n : nullptr, false);
 }
 
 // create_rankings through the fused kernel in RANKS mode (bucket-sort ranking of every gene).

@@ -61,7 +61,8 @@ enum { TIE_ST_FAST = 0, TIE_ST_LONG = 1, TIE_ST_BADVAL = 2, TIE_ST_DUP = 3, TIE_
 struct TieArgs {
     const int64_t* indptr;
     const void* indices;                // int32 (IN_CSR) or uint16 (IN_CSR16 / IN_CSR16_U8)
-    const void* data;                   // float, or uint8 (IN_CSR16_U8)
+    const void* data;                   // float, or uint8 codes (IN_CSR16_U8)
+    const uint32_t* lut;                // IN_CSR16_U8: [256] float bit patterns of the codes
     int64_t n_cells;
     int n_genes, n_words, wpt;          // wpt = ceil(n_words / kTG)
     int cutoff;
@@ -118,17 +119,22 @@ __device__ __forceinline__ uint32_t group_excl_scan(uint32_t v, uint32_t* s_w, i
     return off + incl - v;
 }
 
+// value bits of stored entry i (what orders the entries: for positive floats the bit pattern orders like the value)
 template <int IN> struct TieVal {
     using type = float;
-    static __device__ __forceinline__ uint32_t bits(const float* p, int i) { return __float_as_uint(__ldg(p + i)); }
-};
-template <> struct TieVal<IN_CSR16_U8> {
-    using type = uint8_t;
-    // small integer counts stored as bytes; their float image orders like the counts
-    static __device__ __forceinline__ uint32_t bits(const uint8_t* p, int i) {
-        return __float_as_uint((float)__ldg(p + i));
+    static __device__ __forceinline__ uint32_t bits(const float* p, int64_t i, const uint32_t*) {
+        return __float_as_uint(__ldg(p + i));
     }
 };
+// IN_CSR16_U8: one byte per stored value, an index into a table of up to 256 float bit patterns (the distinct values of
+// the matrix: the host pipeline builds it while it narrows the upload to 3 bytes per entry).  1 KB: it lives in L1.
+template <> struct TieVal<IN_CSR16_U8> {
+    using type = uint8_t;
+    static __device__ __forceinline__ uint32_t bits(const uint8_t* p, int64_t i, const uint32_t* lut) {
+        return __ldg(lut + __ldg(p + i));
+    }
+};
+template <> struct TieVal<IN_CSR_U8> : TieVal<IN_CSR16_U8> {};
 
 // One gene's row of the regulon table: four slots.  Empty slots add zero to one of 32 dummy accumulators (picked by
 // the gene's position, so that a warp's empty slots spread over the banks): the hot loop has no branch per slot.
@@ -223,7 +229,8 @@ constexpr int kTieChainCap = kTieNB * 4 / (kTGW * 8);      // chained rows a war
 // range onto its kTieNB bins; a value outside it lands in an end bin, which the one-value-per-bin check covers.
 template <int IN>
 __global__ void __launch_bounds__(1024) tie_range_kernel(const int64_t* __restrict__ indptr, int64_t n_cells,
-                                                          const void* __restrict__ data, uint32_t* __restrict__ range) {
+                                                          const void* __restrict__ data, const uint32_t* __restrict__ lut,
+                                                          uint32_t* __restrict__ range) {
     using VT = TieVal<IN>;
     const int64_t e0 = indptr[0], total = indptr[n_cells] - e0;
     const typename VT::type* const vals = reinterpret_cast<const typename VT::type*>(data) + e0;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(1024) tie_range_kernel(const int64_t* __restri
     const int64_t n_s = total < 65536 ? total : 65536;
     for (int64_t k = threadIdx.x; k < n_s; k += 1024) {
         const int64_t i = total <= 65536 ? k : (int64_t)(((unsigned __int128)k * (unsigned __int128)total) >> 16);
-        const uint32_t u = VT::bits(vals + i, 0);
+        const uint32_t u = VT::bits(vals, i, lut);
         const bool ps = (u << 1) != 0u && u <= 0x7F800000u;
         umin = min(umin, ps ? u : 0xFFFFFFFFu);
         umax = max(umax, ps ? u : 0u);
@@ -248,6 +255,17 @@ __global__ void __launch_bounds__(1024) tie_range_kernel(const int64_t* __restri
         range[0] = s_min;
         range[1] = s_max;
     }
+}
+
+// codes -> float values for the stored entries of the cells (absolute offsets, like the kernels index them): what the general
+// kernel reads when cells of a byte-coded chunk land on the to-do list.
+template <int IN>
+__global__ void __launch_bounds__(256) tie_decode_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ lut,
+                                                         float* __restrict__ out, const int64_t* __restrict__ indptr,
+                                                         int64_t n_cells) {
+    const int64_t e0 = indptr[0], e1 = indptr[n_cells];
+    for (int64_t i = e0 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < e1; i += (int64_t)gridDim.x * 256)
+        out[i] = __uint_as_float(__ldg(lut + __ldg(codes + i)));
 }
 
 template <int IN, bool UNIT>
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
 #pragma unroll
                 for (int k = 0; k < kTieU; ++k) {
                     const bool in = base + k * kTG < n;
-                    u[k] = in ? VT::bits(vals, base + k * kTG) : 0u;
+                    u[k] = in ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
                     col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
                 }
 #pragma unroll
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
 #pragma unroll
                 for (int k = 0; k < kTieU; ++k) {
                     const bool in = base + k * kTG < n;
-                    u[k] = in ? VT::bits(vals, base + k * kTG) : 0u;
+                    u[k] = in ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
                     col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
                 }
                 bool any_tail = false;

@@ -314,6 +314,28 @@ class AUCellPlan:
         )
         return out
 
+    def aucell_csr_lut8(self, indptr, indices16, codes, lut, out=None, out_nnz=None, scratch=None, stream=None):
+        """CSR with uint16 (or int32) column indices and one-byte value codes into ``lut`` (float32 CUDA tensor, up to 256
+        values): 3 (or 5) bytes per stored entry (``aucell_csr16_lut8_f32`` / ``aucell_csr_lut8_f32``).  ``scratch``:
+        float32 [nnz] work space (allocated if None)."""
+        import torch
+
+        assert indptr.is_cuda and indptr.dtype == torch.int64 and codes.dtype == torch.uint8
+        assert indices16.dtype in (torch.uint16, torch.int16, torch.int32) and lut.dtype == torch.float32 and lut.numel() <= 256
+        fn = self._lib.aucell_csr_lut8_f32 if indices16.dtype == torch.int32 else self._lib.aucell_csr16_lut8_f32
+        n_cells = indptr.numel() - 1
+        if out is None:
+            out = torch.empty((n_cells, self.n_regulons), dtype=torch.float64, device=indptr.device)
+        lut256 = torch.zeros(256, dtype=torch.float32, device=indptr.device)
+        lut256[: lut.numel()] = lut
+        if scratch is None:
+            scratch = torch.empty(max(int(codes.numel()), 1), dtype=torch.float32, device=indptr.device)
+        _native.check(
+            fn(self._handle, indptr.data_ptr(), indices16.data_ptr(), codes.data_ptr(), lut256.data_ptr(),
+               scratch.data_ptr(), n_cells, out.data_ptr(), _torch_ptr(out_nnz), self._stream_ptr(stream))
+        )
+        return out
+
     def rank_dense(self, expr, out=None, out_nnz=None, stream=None):
         """Full ranking rows, uint32 stored in an int32 tensor [n_cells, n_genes], shuffled column order."""
         import torch

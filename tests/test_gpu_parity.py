@@ -576,6 +576,68 @@ def test_tie_class_kernel_equals_general_kernel_bit_for_bit(unweighted, n_genes)
         assert_auc_close(fast.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_byte_coded_values_device_and_host_paths(unweighted, monkeypatch):
+    """3 bytes per stored entry: uint16 column index + one-byte code into a table of the distinct values
+    (aucell_csr16_lut8_f32, what the host pipeline uploads while the matrix holds <= 256 distinct values).  Bit-identical
+    to the float32 entry point -- on the mixed bag of cells too (negatives, NaN, long rows, ... go to the general kernel
+    through the decoded values) --, for dictionaries that grow from chunk to chunk, and when a later chunk overflows
+    the dictionary (the call then continues with float32 values)."""
+    import torch
+
+    n_genes = 9001
+    rs = np.random.RandomState(23)
+    X, m = _mixed_bag_matrix(rs, n_genes)
+    # the continuous row and the hundreds-of-distinct-values row do not fit one byte: drop them for the device-level call
+    keep = [i for i in range(m.shape[0]) if len(np.unique(m[i].data)) <= 60]
+    order = rs.permutation(np.tile(np.asarray(keep), 25))
+    mk = m[order]
+    vals, codes = np.unique(mk.data.view(np.uint32), return_inverse=True)
+    assert len(vals) <= 256
+    reg = synth.make_regulons(rs, n_genes, 90, 10, 300, weighted=not unweighted)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(5).permutation(n_genes)
+    indptr, indices, data = cuda(mk.indptr.astype(np.int64)), cuda(mk.indices.astype(np.int32)), cuda(mk.data)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted=unweighted) as plan:
+        want = plan.aucell_csr(indptr, indices, data)
+        shuffled = rs.permutation(len(vals))                     # codes need not be ordered
+        inv = np.empty_like(shuffled); inv[shuffled] = np.arange(len(vals))
+        got = plan.aucell_csr_lut8(indptr, indices.to(torch.uint16), cuda(inv[codes].astype(np.uint8)),
+                                   cuda(vals[shuffled].view(np.float32)))
+        assert torch.equal(got, want)
+        plan.set_fast_path(False)                                # every cell through the decoded values
+        assert torch.equal(plan.aucell_csr_lut8(indptr, indices.to(torch.uint16), cuda(inv[codes].astype(np.uint8)),
+                                                cuda(vals[shuffled].view(np.float32))), want)
+        plan.set_fast_path(True)
+        # host pipeline: the whole bag (the continuous row overflows the dictionary in whatever chunk it sits)
+        order2 = rs.permutation(np.tile(np.arange(m.shape[0]), 25))
+        m2 = m[order2]
+        ip2, ix2, dv2 = m2.indptr.astype(np.int64), m2.indices.astype(np.int32), m2.data.astype(np.float32)
+        want_nnz2 = torch.empty(m2.shape[0], dtype=torch.int32, device="cuda")
+        want2 = plan.aucell_csr(cuda(ip2), cuda(ix2), cuda(dv2), out_nnz=want_nnz2).cpu().numpy()
+        want_nnz2 = want_nnz2.cpu().numpy()
+        results = {}
+        for mode in ("0", "1", None):
+            if mode is None:
+                monkeypatch.delenv("AUCELL_B200_HOST_VAL8", raising=False)
+            else:
+                monkeypatch.setenv("AUCELL_B200_HOST_VAL8", mode)
+            for chunk in (0, 37):
+                got2, nnz2 = plan.aucell_csr_host(ip2, ix2, dv2, want_nnz=True, chunk_cells=chunk)
+                assert np.array_equal(got2, want2), (mode, chunk)
+                assert np.array_equal(nnz2, want_nnz2), (mode, chunk)
+                results[(mode, chunk)] = plan.last_host_bytes()[0]
+        # count-like rows only: the byte codes really are what goes up (3 bytes per entry + the tables)
+        mk_ip, mk_ix, mk_dv = mk.indptr.astype(np.int64), mk.indices.astype(np.int32), mk.data.astype(np.float32)
+        monkeypatch.setenv("AUCELL_B200_HOST_VAL8", "1")
+        got3 = plan.aucell_csr_host(mk_ip, mk_ix, mk_dv, chunk_cells=64)
+        sent = plan.last_host_bytes()[0]
+        assert np.array_equal(got3, want.cpu().numpy())
+        n_chunks = -(-mk.shape[0] // 64)
+        assert sent == 8 * (mk.shape[0] + n_chunks) + 3 * mk.nnz + 1024 * n_chunks
+    monkeypatch.delenv("AUCELL_B200_HOST_VAL8", raising=False)
+
+
 @pytest.mark.parametrize("thr,unweighted", [(0.05, False), (0.6, False), (0.6, True)])
 def test_from_rankings_hit_list_and_its_overflow(thr, unweighted):
     """aucell4r kernel: ranks below the cutoff are collected into a 4,096-entry list before they are scattered; with
