@@ -159,6 +159,12 @@ int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_
 int aucell_rss_f64(int device, const double* d_auc, int64_t n_cells, int64_t row_stride, int32_t n_regulons,
                    const int32_t* d_labels, int32_t n_types, const int64_t* h_type_counts, double* d_out, void* stream);
 
+/* Non-zero entries per cell of a CSR matrix -- np.count_nonzero(ex_mtx, axis=1), what pyscenic.aucell.derive_auc_threshold
+ * takes its quantiles of (reference src/pyscenic/aucell.py:54-72): NaN counts as non-zero, an explicit +-0.0 does not.
+ * (The aucell_* entry points deliver the same numbers through d_out_nnz as a by-product.) */
+int aucell_count_nonzero_csr_f32(int device, const int64_t* d_indptr, const float* d_data, int64_t n_cells,
+                                 int32_t* d_out_nnz, void* stream);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 /* Bytes the last aucell_*_host call on this plan moved over PCIe: out2 = { host-to-device, device-to-host }.  (The CSR
  * call uploads uint16 column indices when n_genes <= 65535, so this can be less than the size of the caller's arrays.) */

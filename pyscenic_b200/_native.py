@@ -59,6 +59,7 @@ EXPORTED_SYMBOLS = [
     "aucell_plan_path_stats",
     "aucell_plan_last_host_bytes",
     "aucell_rss_f64",
+    "aucell_count_nonzero_csr_f32",
     "aucell_csr16_lut8_f32",
     "aucell_csr_lut8_f32",
     "aucell_plan_set_fast_path",
@@ -211,6 +212,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_plan_fast_stats.restype = c_int
         lib.aucell_rss_f64.argtypes = [c_int, p, i64, i64, i32, p, i32, p, p, p]
         lib.aucell_rss_f64.restype = c_int
+        lib.aucell_count_nonzero_csr_f32.argtypes = [c_int, p, p, i64, p, p]
+        lib.aucell_count_nonzero_csr_f32.restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]
         lib.aucell_plan_destroy.restype = c_int
         for name in ("aucell_rank_dense_f32", "aucell_rank_dense_f64"):

@@ -262,11 +262,38 @@ def create_rankings(ex_mtx: pd.DataFrame, seed=None, *, device: int = 0) -> pd.D
     return pd.DataFrame(data=out, index=ex_mtx.index, columns=ex_mtx.columns[perm])
 
 
-def derive_auc_threshold(ex_mtx: pd.DataFrame) -> pd.Series:
+def derive_auc_threshold(ex_mtx, *, device: int = 0) -> pd.Series:
     """
     Derive AUC thresholds for an expression matrix (reference ``aucell.py:54-72``): quantiles over cells of the
     fraction of detected (non-zero) genes.
+
+    :param ex_mtx: The expression profile matrix (n_cells x n_genes): a DataFrame / array as in the reference, or a
+        ``scipy.sparse`` matrix -- its stored values are counted on the GPU (``aucell_count_nonzero_csr_f32``; an
+        explicit zero does not count, NaN does, like ``np.count_nonzero``) without densifying.
+    :return: A pandas Series with the AUC thresholds at the 1 %, 5 %, 10 %, 50 % and 100 % quantiles.
     """
+    if _is_sparse(ex_mtx):
+        import ctypes
+
+        import torch
+
+        csr = ex_mtx.tocsr()
+        dev = _torch_device(device)
+        lib = _native.load()
+        n_cells = csr.shape[0]
+        counts = np.zeros(n_cells, dtype=np.int32)
+        if n_cells and csr.nnz:
+            values = np.asarray(csr.data)
+            if values.dtype != np.float32:
+                values = (values != 0).astype(np.float32)           # only "is it zero" matters; keeps NaN non-zero
+            d_ip = _from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(dev)
+            d_dv = _from_numpy(np.ascontiguousarray(values)).to(dev)
+            d_out = torch.empty(n_cells, dtype=torch.int32, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.aucell_count_nonzero_csr_f32(device, d_ip.data_ptr(), d_dv.data_ptr(), n_cells,
+                                                           d_out.data_ptr(), ctypes.c_void_p(st)))
+            counts = d_out.cpu().numpy()
+        return pd.Series(counts).quantile([0.01, 0.05, 0.10, 0.50, 1]) / csr.shape[1]
     return pd.Series(np.count_nonzero(ex_mtx, axis=1)).quantile([0.01, 0.05, 0.10, 0.50, 1]) / ex_mtx.shape[1]
 
 

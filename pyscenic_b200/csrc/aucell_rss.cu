@@ -88,7 +88,35 @@ __global__ void __launch_bounds__(kRssThreads) rss_finish_kernel(const double* _
     out[(int64_t)t * n_reg + r] = 1.0 - sqrt(js < 0.0 ? 0.0 : js);   // rounding can leave js = -1e-17 when p == q; NaN (all-zero regulon) passes through
 }
 
+// np.count_nonzero per row of a CSR matrix (derive_auc_threshold, reference aucell.py:67): NaN counts, -0.0 does not.
+// One warp per row.
+__global__ void __launch_bounds__(256) count_nonzero_csr_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ data,
+                                                                 int64_t n_rows, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (int64_t)gridDim.x * 8) {
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        int c = 0;
+        for (int64_t i = b + lane; i < e; i += 32) c += (data[i] != 0.0f) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) out[row] = c;
+    }
+}
+
 }  // namespace
+
+extern "C" int aucell_count_nonzero_csr_f32(int device, const int64_t* d_indptr, const float* d_data, int64_t n_cells,
+                                            int32_t* d_out_nnz, void* stream) {
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (n_cells == 0) return AUCELL_OK;
+    if (!d_indptr || !d_out_nnz) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    const int grid = (int)std::min<int64_t>((n_cells + 7) / 8, 148 * 16);
+    count_nonzero_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_indptr, d_data, n_cells, d_out_nnz);
+    launch_counter().fetch_add(1);
+    CK(cudaGetLastError());
+    return AUCELL_OK;
+}
 
 extern "C" int aucell_rss_f64(int device, const double* d_auc, int64_t n_cells, int64_t row_stride, int32_t n_regulons,
                               const int32_t* d_labels, int32_t n_types, const int64_t* h_type_counts, double* d_out,

@@ -464,6 +464,73 @@ def test_config3_full_size_properties_and_spot_check():
     assert_auc_close(av[pick], oracle_auc(X, perm, reg, cutoff))
 
 
+def _full_size_check(n_cells, n_genes, mean_nnz, n_regulons, thr, seed, n_sample=2048):
+    """Shared body of the full-size parity tests: run-to-run bit identity, the tie-class kernel against the general
+    kernel on EVERY cell, value range, and a random sample of cells against the CPU oracle."""
+    import torch
+
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, mean_nnz, seed=seed, device="cuda")
+    rs = np.random.RandomState(seed)
+    reg = synth.make_regulons(rs, n_genes, n_regulons, 10, 400, weighted=True, repressors=True)
+    cutoff = O.derive_rank_cutoff(thr, n_genes)
+    perm = np.random.RandomState(42).permutation(n_genes)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        a = plan.aucell_csr(indptr, indices, data)
+        fast = plan.fast_stats()
+        assert torch.equal(plan.aucell_csr(indptr, indices, data), a)          # deterministic
+        plan.set_fast_path(False)
+        assert torch.equal(plan.aucell_csr(indptr, indices, data), a)          # both kernels, every cell, every bit
+        plan.set_fast_path(True)
+    assert fast["ranked"] > 0.9 * n_cells
+    assert bool(torch.isfinite(a).all()) and float(a.min()) >= 0.0 and float(a.max()) < 1.0
+    pick = np.sort(np.random.RandomState(seed + 1).choice(n_cells, n_sample, replace=False))
+    ip = indptr.cpu().numpy()
+    ix, dv = indices.cpu().numpy(), data.cpu().numpy()
+    X = np.zeros((len(pick), n_genes), dtype=np.float32)
+    for r, c in enumerate(pick):
+        X[r, ix[ip[c]:ip[c + 1]]] = dv[ip[c]:ip[c + 1]]
+    assert_auc_close(a[torch.from_numpy(pick).cuda()].cpu().numpy(), oracle_auc(X, perm, reg, cutoff))
+
+
+def test_config4_shape_200k_cells_full_parity():
+    """BASELINE.json configs[3] (the benchmark's shape: 27,998 genes, ~1,960 stored entries per cell, 500 weighted
+    regulons incl. (-), threshold 0.05) on 200 k cells."""
+    _full_size_check(200_000, 27_998, 1960, 500, 0.05, seed=404)
+
+
+@pytest.mark.parametrize("thr,n_regulons", [(0.01, 50), (0.01, 2000), (0.2, 50), (0.2, 2000)])
+def test_config5_corners_200k_cells_full_parity(thr, n_regulons):
+    """BASELINE.json configs[4]: the corners of the threshold (0.01 .. 0.2) x regulon-count (50 .. 2,000) sweep on
+    200 k cells x 20 k genes."""
+    _full_size_check(200_000, 20_000, 1400, n_regulons, thr, seed=500 + n_regulons + int(thr * 100))
+
+
+def test_derive_auc_threshold_dense_golden_and_sparse():
+    """pyscenic_b200.aucell.derive_auc_threshold itself (not the oracle's copy): the reference's quantiles on the golden
+    adversarial matrix (NaN counts as non-zero, -0.0 does not), and the same numbers from a scipy CSR matrix whose
+    stored entries include explicit zeros (counted on the GPU, aucell_count_nonzero_csr_f32)."""
+    import scipy.sparse as sp
+
+    from pyscenic_b200.aucell import derive_auc_threshold
+
+    A = GOLD["adv_expr"]
+    got = derive_auc_threshold(frame(A))
+    assert np.array_equal(got.values, GOLD["adv_auc_threshold_quantiles"])
+    assert list(got.index) == [0.01, 0.05, 0.10, 0.50, 1]
+    m = sp.csr_matrix(np.nan_to_num(A, nan=7.0))         # (scipy drops nothing: NaN would be kept as a stored entry too)
+    m.data[::5] = 0.0                                    # explicit zeros among the stored entries
+    m.data[3::11] = np.nan
+    dense = m.toarray()
+    want = pd.Series(np.count_nonzero(dense, axis=1)).quantile([0.01, 0.05, 0.10, 0.50, 1]) / dense.shape[1]
+    got_s = derive_auc_threshold(m)
+    assert np.array_equal(got_s.values, want.values)
+    rs = np.random.RandomState(1)
+    big = sp.random(3000, 5000, density=0.07, format="csr", random_state=rs, dtype=np.float32)
+    want_b = pd.Series(np.diff(big.indptr)).quantile([0.01, 0.05, 0.10, 0.50, 1]) / 5000
+    assert np.array_equal(derive_auc_threshold(big).values, want_b.values)
+    assert np.array_equal(derive_auc_threshold(big.astype(np.float64)).values, want_b.values)
+
+
 @pytest.mark.parametrize("n_genes", [60000, 70001])
 def test_deep_cells_whose_selection_exceeds_the_register_capacity(n_genes):
     """Cells with more stored entries than the register capacity (4,096) whose tie class at the cutoff is so large
