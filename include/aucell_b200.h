@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -158,6 +158,29 @@ int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_
  * A regulon whose AUCs are all zero yields NaN, as in the reference. */
 int aucell_rss_f64(int device, const double* d_auc, int64_t n_cells, int64_t row_stride, int32_t n_regulons,
                    const int32_t* d_labels, int32_t n_types, const int64_t* h_type_counts, double* d_out, void* stream);
+
+/* Binarization of an AUC matrix (replaces pyscenic.binarization.derive_threshold / binarize, reference
+ * src/pyscenic/binarization.py:12-98), all regulons at once.  d_cols: device fp64 [n_regulons x n_cells], row r = the AUC
+ * values of regulon r (the transposed AUC matrix); "sorted" entry points need every row in ascending order.  Asynchronous
+ * on `stream`, deterministic (no atomics).
+ *   stats   d_out4[r]  = { mean, variance (ddof 0), variance (ddof 1), 0 }                      -> mean + 2 std
+ *   dip     d_out_dip[r] = Hartigan's dip statistic of row r; d_scratch: int32 [n_regulons x 4 x (n_cells + 1)]
+ *   gmm2    two-component Gaussian mixture by EM with sklearn's update rules, started from the hard assignment
+ *           "the first d_split[r] sorted values are component 0"; d_out9[r] = { w0, w1, mean0, mean1, var0, var1,
+ *           mean log-likelihood under the final parameters, iterations, converged }
+ *   trough  scipy's bounded Brent minimiser of the Gaussian kernel density of row r (kernel variance d_kde_var[r])
+ *           between d_lo[r] and d_hi[r]; d_out_x[r] = the minimiser
+ */
+int aucell_binarize_stats_f64(int device, const double* d_cols, int32_t n_regulons, int64_t n_cells, double* d_out4,
+                              void* stream);
+int aucell_binarize_dip_f64(int device, const double* d_sorted_cols, int32_t n_regulons, int64_t n_cells,
+                            int32_t* d_scratch, double* d_out_dip, void* stream);
+int aucell_binarize_gmm2_f64(int device, const double* d_sorted_cols, int32_t n_regulons, int64_t n_cells,
+                             const int32_t* d_split, int32_t max_iter, double tol, double reg_covar, double* d_out9,
+                             void* stream);
+int aucell_binarize_trough_f64(int device, const double* d_cols, int32_t n_regulons, int64_t n_cells, const double* d_lo,
+                               const double* d_hi, const double* d_kde_var, double xatol, int32_t maxiter,
+                               double* d_out_x, void* stream);
 
 /* Non-zero entries per cell of a CSR matrix -- np.count_nonzero(ex_mtx, axis=1), what pyscenic.aucell.derive_auc_threshold
  * takes its quantiles of (reference src/pyscenic/aucell.py:54-72): NaN counts as non-zero, an explicit +-0.0 does not.

@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 ]
 # translation units of the library (compiled in parallel, then linked into one shared object)
 TRANSLATION_UNITS = ["aucell_b200.cu", "aucell_f32_dense.cu", "aucell_f32_csr.cu", "aucell_f64_dense.cu",
-                     "aucell_f64_csr.cu", "aucell_f32_csr16.cu", "aucell_rss.cu"]
+                     "aucell_f64_csr.cu", "aucell_f32_csr16.cu", "aucell_rss.cu", "aucell_binarize.cu"]
 
 # every symbol include/aucell_b200.h declares (tests check that the library exports each of them)
 EXPORTED_SYMBOLS = [
@@ -60,6 +60,10 @@ EXPORTED_SYMBOLS = [
     "aucell_plan_last_host_bytes",
     "aucell_rss_f64",
     "aucell_count_nonzero_csr_f32",
+    "aucell_binarize_stats_f64",
+    "aucell_binarize_dip_f64",
+    "aucell_binarize_gmm2_f64",
+    "aucell_binarize_trough_f64",
     "aucell_csr16_lut8_f32",
     "aucell_csr_lut8_f32",
     "aucell_plan_set_fast_path",
@@ -214,6 +218,14 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_rss_f64.restype = c_int
         lib.aucell_count_nonzero_csr_f32.argtypes = [c_int, p, p, i64, p, p]
         lib.aucell_count_nonzero_csr_f32.restype = c_int
+        f64 = ctypes.c_double
+        lib.aucell_binarize_stats_f64.argtypes = [c_int, p, i32, i64, p, p]
+        lib.aucell_binarize_dip_f64.argtypes = [c_int, p, i32, i64, p, p, p]
+        lib.aucell_binarize_gmm2_f64.argtypes = [c_int, p, i32, i64, p, i32, f64, f64, p, p]
+        lib.aucell_binarize_trough_f64.argtypes = [c_int, p, i32, i64, p, p, p, f64, i32, p, p]
+        for name in ("aucell_binarize_stats_f64", "aucell_binarize_dip_f64", "aucell_binarize_gmm2_f64",
+                     "aucell_binarize_trough_f64"):
+            getattr(lib, name).restype = c_int
         lib.aucell_plan_destroy.argtypes = [p]
         lib.aucell_plan_destroy.restype = c_int
         for name in ("aucell_rank_dense_f32", "aucell_rank_dense_f64"):
