@@ -165,22 +165,6 @@ def guess_separator(fname: str) -> str:
     raise ValueError('Unknown file format "{}".'.format(fname))
 
 
-def _load_yaml(fname: str):
-    import yaml
-
-    with openfile(fname, "r") as f:
-        docs = yaml.safe_load(f)
-    out = []
-    for d in docs:
-        g2w = d["gene2weight"]
-        if "transcription_factor" in d:
-            out.append(Regulon(name=d["name"], gene2weight=g2w, transcription_factor=d["transcription_factor"],
-                               context=frozenset(d.get("context", ())), score=d.get("score", 0.0)))
-        else:
-            out.append(GeneSignature(name=d["name"], gene2weight=g2w))
-    return out
-
-
 def save_to_yaml(signatures: Sequence[GeneSignature], fname: str) -> None:
     import yaml
 
@@ -194,19 +178,124 @@ def save_to_yaml(signatures: Sequence[GeneSignature], fname: str) -> None:
         yaml.safe_dump(docs, f)
 
 
+# ---- cisTarget motif-enrichment tables -> regulons ---------------------------------------------------------------
+# `pyscenic aucell expr.loom reg.csv` is the standard invocation: the signatures file is the table `pyscenic ctx`
+# writes.  Reference: cli/utils.py:205-227 (load_signatures), utils.py:438-456 (load_motifs), transform.py:382-536
+# (df2regulons / _regulon4group).  Only what AUCell needs is kept: one regulon per (TF, activating / repressing), the
+# union of the target genes of its enriched motifs with the largest weight per gene.
+COLUMN_NAME_TF = "TF"
+COLUMN_NAME_MOTIF_ID = "MotifID"
+COLUMN_NAME_NES = "NES"
+COLUMN_NAME_CONTEXT = "Context"
+COLUMN_NAME_TARGET_GENES = "TargetGenes"
+COLUMN_NAME_MOTIF_SIMILARITY_QVALUE = "MotifSimilarityQvalue"
+COLUMN_NAME_ORTHOLOGOUS_IDENTITY = "OrthologousIdentity"
+ACTIVATING_MODULE = "activating"
+REPRESSING_MODULE = "repressing"
+
+
+def _literal(text):
+    """The table stores Python literals (``frozenset({...})`` contexts, ``[(gene, weight), ...]`` target genes); the
+    reference ``eval``s them.  Here only literals are accepted."""
+    import ast
+
+    t = text.strip()
+    if t.startswith("frozenset(") and t.endswith(")"):
+        inner = t[len("frozenset("):-1].strip()
+        return frozenset(ast.literal_eval(inner)) if inner else frozenset()
+    return ast.literal_eval(t)
+
+
+def load_motifs(fname: str, sep: str = ",") -> pd.DataFrame:
+    """The enriched-motifs table of ``pyscenic ctx`` (two header rows, index (TF, MotifID))."""
+    df = pd.read_csv(fname, sep=sep, index_col=[0, 1], header=[0, 1], skipinitialspace=True)
+    df[("Enrichment", COLUMN_NAME_CONTEXT)] = df[("Enrichment", COLUMN_NAME_CONTEXT)].apply(_literal)
+    df[("Enrichment", COLUMN_NAME_TARGET_GENES)] = df[("Enrichment", COLUMN_NAME_TARGET_GENES)].apply(_literal)
+    return df
+
+
+def df2regulons(df: pd.DataFrame) -> Sequence[Regulon]:
+    """Regulons from a table of enriched motifs: rows are grouped per TF and interaction type; a group's target genes
+    are united keeping the maximum weight per gene, its score is the best combined score of its motifs."""
+    import math
+
+    assert not df.empty, "Signatures dataframe is empty!"
+    df = df.copy()
+    if df.columns.nlevels == 2:
+        df.columns = df.columns.droplevel(0)
+
+    def score(nes, qval, ident):
+        fraction = 1.0
+        try:
+            fraction = min(-math.log(qval, 10), 10) / 10 if not math.isnan(qval) else 1.0
+        except ValueError:          # math domain error: q-value 0
+            pass
+        s = nes * fraction
+        return s if math.isnan(ident) else s * ident
+
+    regulons = []
+    kinds = df[COLUMN_NAME_CONTEXT].apply(lambda ctx: REPRESSING_MODULE if REPRESSING_MODULE in ctx else ACTIVATING_MODULE)
+    tfs = df.index.get_level_values(COLUMN_NAME_TF)
+    for (tf_name, kind), grp in df.groupby([tfs, kinds.values], sort=True):
+        context = frozenset([kind])
+        name = "{}{}".format(tf_name, "(-)" if kind == REPRESSING_MODULE else "(+)")
+        top = grp.sort_values(by=COLUMN_NAME_NES, ascending=False).head(1)
+        motif_logo = "{}.png".format(top.index.get_level_values(COLUMN_NAME_MOTIF_ID)[0])
+        merged = None
+        for _, row in grp.iterrows():
+            targets = row[COLUMN_NAME_TARGET_GENES]
+            reg = Regulon(name=name, gene2weight=dict(targets) if not isinstance(targets, dict) else targets,
+                          transcription_factor=tf_name, context=context,
+                          score=score(float(row[COLUMN_NAME_NES]),
+                                      float(row.get(COLUMN_NAME_MOTIF_SIMILARITY_QVALUE, float("nan"))),
+                                      float(row.get(COLUMN_NAME_ORTHOLOGOUS_IDENTITY, float("nan")))))
+            merged = reg if merged is None else merged.union(reg)
+        regulons.append(merged.copy(context=frozenset(set(context) | {motif_logo})))
+    return regulons
+
+
+def _load_yaml(fname: str):
+    """YAML signatures: this package's own plain layout (a list of mappings), or the reference's ``yaml.dump`` of
+    signature objects (``!GeneSignature`` / ``!Regulon`` tagged mappings with ``genes`` / ``weights`` lists)."""
+    import yaml
+
+    def build(d):
+        if "gene2weight" in d:
+            g2w = d["gene2weight"]
+        else:
+            genes, weights = list(d.get("genes", ())), d.get("weights")
+            g2w = dict(zip(genes, weights)) if weights is not None else genes
+        if d.get("transcription_factor"):
+            return Regulon(name=d["name"], gene2weight=g2w, transcription_factor=d["transcription_factor"],
+                           context=frozenset(d.get("context", ()) or ()), score=d.get("score", 0.0) or 0.0)
+        return GeneSignature(name=d["name"], gene2weight=g2w)
+
+    class _Loader(yaml.SafeLoader):
+        pass
+
+    def tagged(loader, suffix, node):
+        return build(loader.construct_mapping(node, deep=True))
+
+    _Loader.add_multi_constructor("!", tagged)
+    _Loader.add_multi_constructor("tag:yaml.org,2002:python/object", tagged)
+    with openfile(fname, "r") as f:
+        docs = yaml.load(f, Loader=_Loader)
+    return [d if isinstance(d, GeneSignature) else build(d) for d in docs]
+
+
 def load_signatures(fname: str) -> Sequence[GeneSignature]:
     """
-    Load gene signatures: GMT, DAT (pickled list of signatures) or YAML.
+    Load genes signatures from disk.
 
-    The reference additionally turns a cisTarget motif-enrichment table (csv/tsv) into regulons via
-    ``pyscenic.transform.df2regulons``; that belongs to the ``ctx`` step and is not part of this package.
+    Supported file formats are GMT, DAT (pickled), YAML or CSV / TSV (enriched motifs), as in the reference
+    (``cli/utils.py:205-227``).
+
+    :param fname: The name of the file that contains the signatures.
+    :return: A list of gene signatures.
     """
     extension = PurePath(fname).suffixes
     if ".csv" in extension or ".tsv" in extension:
-        raise ValueError(
-            'Unknown file format "{}": motif-enrichment tables must be converted to regulons by `pyscenic ctx` '
-            "tooling first (gmt, dat and yaml signatures are supported).".format(fname)
-        )
+        return df2regulons(load_motifs(fname, sep=suffixes_to_separator(extension)))
     if ".yaml" in extension or ".yml" in extension:
         return _load_yaml(fname)
     if ".gmt" in extension:

@@ -45,6 +45,43 @@ def test_parser_has_the_reference_flag_surface(tmp_path):
     assert p.parse_args(["@" + str(argsfile)]).seed == 5
 
 
+def _write_ctx_table(path, sep=","):
+    """A motif-enrichment table laid out like `pyscenic ctx` writes it (two header rows, (TF, MotifID) index, Python
+    literals in the Context / TargetGenes cells): the usual signatures file of `pyscenic aucell`."""
+    nan = float("nan")
+    rows = [("TFa", "m1", 0.1, 3.5, 1e-4, nan, "ann", frozenset({"activating", "weight>75.0%"}), [("g1", 2.0), ("g2", 1.0)], 10),
+            ("TFa", "m2", 0.2, 4.5, nan, 0.8, "ann", frozenset({"activating", "top50"}), [("g2", 3.0), ("g3", 0.5)], 12),
+            ("TFa", "m3", 0.2, 3.1, nan, nan, "ann", frozenset({"repressing", "top50"}), [("g9", 1.5), ("g7", 0.25)], 12),
+            ("TFb", "m4", 0.3, 5.0, 0.0, nan, "ann", frozenset({"activating"}), [("g4", 1.0), ("g1", 4.0)], 3)]
+    idx = pd.MultiIndex.from_tuples([(r[0], r[1]) for r in rows], names=["TF", "MotifID"])
+    cols = pd.MultiIndex.from_tuples([("Enrichment", c) for c in ["AUC", "NES", "MotifSimilarityQvalue", "OrthologousIdentity",
+                                                                  "Annotation", "Context", "TargetGenes", "RankAtMax"]])
+    pd.DataFrame([r[2:] for r in rows], index=idx, columns=cols).to_csv(path, sep=sep)
+
+
+def test_signatures_from_a_ctx_motif_table_and_reference_yaml(tmp_path):
+    """reference cli/utils.py:205-227: csv / tsv signatures are cisTarget tables (-> df2regulons); yaml files may hold the
+    reference's tagged signature objects."""
+    for ext, sep in ((".csv", ","), (".tsv", "\t")):
+        f = str(tmp_path / ("reg" + ext))
+        _write_ctx_table(f, sep)
+        regs = load_signatures(f)
+        assert [r.name for r in regs] == ["TFa(+)", "TFa(-)", "TFb(+)"]
+        assert all(isinstance(r, Regulon) for r in regs)
+        # union of the motifs' target genes, the largest weight per gene
+        assert dict(regs[0].gene2weight) == {"g1": 2.0, "g2": 3.0, "g3": 0.5} and regs[0].transcription_factor == "TFa"
+        assert dict(regs[1].gene2weight) == {"g9": 1.5, "g7": 0.25} and "repressing" in regs[1].context
+        assert "m2.png" in regs[0].context and abs(regs[0].score - 4.5 * 0.8) < 1e-12     # best combined score
+        assert abs(regs[2].score - 5.0) < 1e-12                                           # q-value 0: no penalty
+    yml = tmp_path / "ref.yaml"
+    yml.write_text("- !GeneSignature\n  name: s1\n  genes: [g1, g2]\n  weights: [1.0, 2.5]\n"
+                   "- !Regulon\n  name: TFz(+)\n  genes: [g3]\n  weights: [0.75]\n  transcription_factor: TFz\n"
+                   "  context: [activating]\n  score: 2.0\n")
+    back = load_signatures(str(yml))
+    assert back[0].name == "s1" and back[0]["g2"] == 2.5 and not isinstance(back[0], Regulon)
+    assert isinstance(back[1], Regulon) and back[1].transcription_factor == "TFz" and back[1]["g3"] == 0.75
+
+
 def test_matrix_and_signature_io(tmp_path):
     df, sigs, expr, gmt = _write_inputs(tmp_path)
     back = load_exp_matrix(expr)
@@ -65,8 +102,6 @@ def test_matrix_and_signature_io(tmp_path):
     back = load_signatures(yml)
     assert isinstance(back[0], Regulon) and back[0]["g2"] == 2.0 and back[0].transcription_factor == "TF1"
     assert back[1] == sigs[0]
-    with pytest.raises(ValueError):
-        load_signatures(str(tmp_path / "motifs.csv"))
     with pytest.raises(ValueError):
         load_signatures(str(tmp_path / "x.json"))
     out = str(tmp_path / "m.tsv")
