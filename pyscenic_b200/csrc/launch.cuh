@@ -188,7 +188,7 @@ struct TieLayout { int group_stride, groups, smem; };
 inline TieLayout tie_layout(const aucell_plan* p, TieArgs& a, int cap) {
     const int ip_bytes = align16(((p->n_genes + 7) / 8) * 16);
     int off = 0;
-    a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16 + 16);     // + the spare word invalid lanes OR into
+    a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16 + 128);    // + 32 spare words invalid lanes OR into
     a.o_wpre = off; off = align16(off + p->n_words * 2);
     a.o_rep = off; off = align16(off + (kTieNB + 4) * 4);                   // + the spare bin
     a.o_code = off; off = align16(off + kTieNB);
@@ -232,7 +232,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     CK(cudaMemsetAsync(*todo_n, 0, sizeof(int32_t), st));
     a.indptr = indptr; a.indices = indices; a.data = data; a.lut = lut;
     a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.wpt = (p->n_words + kTG - 1) / kTG;
+    a.wpt = ((p->n_words + kTG - 1) / kTG) | 1;          // words per thread in P2: odd, so that a warp's reads spread over the banks
     a.cutoff = (int)p->rank_cutoff;
     a.inv_perm = p->d_inv_perm16;
     a.ell_w = p->d_ell_w; a.xw = p->d_xw; a.ell_u = p->d_ell_u; a.xu = p->d_xu;

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
     uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + a.o_rep);      // [kTieNB + 4] value bits of the bin, 0 = empty;
                                                                           // from P6 on: the warps' chain lists
     uint8_t* const code_of = reinterpret_cast<uint8_t*>(gb + a.o_code);   // [kTieNB] class of the bin
-    uint16_t* const bpp = reinterpret_cast<uint16_t*>(gb + a.o_bpp);      // [cap + 1] position of the j-th entry
+    uint16_t* const bpp = reinterpret_cast<uint16_t*>(gb + a.o_bpp);      // [cap + 1] position of the j-th entry (chunk-interleaved)
     uint8_t* const bpc = reinterpret_cast<uint8_t*>(gb + a.o_bpc);        // [cap + 1] its class
     uint32_t* const cnt = reinterpret_cast<uint32_t*>(gb + a.o_cnt);      // [kTieD][kTG] counters, then bases
     uint2* const fix = reinterpret_cast<uint2*>(gb + a.o_fix);            // [kTieFix] (value bits, pos) of the tail
@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
 
     const int barid = 1 + grp;
     const int n_genes = a.n_genes, n_words = a.n_words, cutoff = a.cutoff, R = a.n_regulons, cap = a.cap;
-    const int dummy_word = (n_words + 3) & ~3;             // a word of A behind the bitmap: invalid lanes OR 0 into it
+    // lanes without an entry OR 0 into a spare word behind the bitmap and add 0 to a counter of the tail class: one
+    // spare PER LANE -- 32 lanes hitting one address would serialise the atomic 32-way
+    const int dummy_word = ((n_words + 3) & ~3) + lane;
     const uint32_t maskL = UNIT ? 0u : ((1u << a.L) - 1u);
     // dummy accumulator of this lane (rows that continue in a chain; unit: index, weighted: byte offset)
     const uint32_t dummy = UNIT ? (uint32_t)(a.acc_words - 32 + lane) : (uint32_t)(a.acc_words - 64 + 2 * lane) * 4u;
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         // ---------------- clear the cell's working set -----------------------------------------------------------
         {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = gtid; i < ((n_words + 4) >> 2); i += kTG) reinterpret_cast<uint4*>(A)[i] = z;
+            for (int i = gtid; i < ((n_words + 3) >> 2); i += kTG) reinterpret_cast<uint4*>(A)[i] = z;
 #pragma unroll
             for (int i = gtid; i < kTieNB / 4; i += kTG) reinterpret_cast<uint4*>(rep)[i] = z;
 #pragma unroll
@@ -480,10 +482,12 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                     const uint32_t jv = (uint32_t)wpre[w] + (uint32_t)__popc(A[w] & ((1u << (pos & 31)) - 1u));
                     const uint32_t bin = bin_of(u[k]);
                     const uint32_t cls = valid ? (uint32_t)code_of[bin] : 0u;
-                    const uint32_t j = valid ? jv : (uint32_t)cap;         // the spare slot behind the arrays
+                    // by_pos is stored chunk-interleaved -- item k of chunk c at k * kTG + c --, so that the threads of a
+                    // warp (one chunk each) read neighbouring elements in P6 instead of elements `ch` apart
+                    const uint32_t chunk = valid ? ((jv * magic) >> 20) : (uint32_t)lane;
+                    const uint32_t j = valid ? (jv - chunk * (uint32_t)ch) * kTG + chunk : (uint32_t)cap;   // else: the spare slot
                     bpp[j] = (uint16_t)pos;
                     bpc[j] = (uint8_t)cls;
-                    const uint32_t chunk = valid ? ((jv * magic) >> 20) : 0u;
                     atomicAdd(&cnt[cls * kTG + chunk], valid ? 1u : 0u);
                     mixed |= (valid && cls != 0u && rep[bin] != u[k]) ? 1u : 0u;   // two values in one class bin
                     any_tail |= valid && cls == 0u;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
 #pragma unroll
                 for (int k = 0; k < kTieP6; ++k) {
                     const bool in = j + k < j1;
-                    const int jj = in ? j + k : cap;
+                    const int jj = in ? (it * kTieP6 + k) * kTG + gtid : cap;
                     const unsigned pos = bpp[jj];
                     const unsigned cc = bpc[jj];
                     uint32_t* const ctr = cnt + cc * kTG + gtid;
