@@ -342,6 +342,42 @@ def run_ours(args, rank, world, local_rank):
         same = bool(torch.equal(h_out.to(dev), out[:n_e2e]))
         e2e["matches_device_path"] = same
 
+    # ---- the call a user makes: pyscenic_b200.aucell.aucell(...) from ordinary (pageable) numpy / pandas memory --------
+    e2e_api = None
+    if world == 1 and w["kind"] == "csr" and not args.no_e2e and not args.no_api:
+        import pandas as pd
+        import scipy.sparse as sp
+
+        from pyscenic_b200.aucell import aucell as api_aucell
+
+        n_api = int(min(n_cells, args.api_cells))
+        e_end = int(indptr[n_api].item())
+        csr = sp.csr_matrix((data[:e_end].cpu().numpy(), indices[:e_end].cpu().numpy(), indptr[: n_api + 1].cpu().numpy()),
+                            shape=(n_api, n_genes))
+        gene_names = ["g%d" % j for j in range(n_genes)]
+        sigs = synth.regulons_to_signatures(*reg)
+        api_aucell(csr[:2048], sigs, auc_threshold=AUC_THRESHOLD, seed=SEED, genes=gene_names)      # warm-up
+        t0 = time.perf_counter()
+        got_api = api_aucell(csr, sigs, auc_threshold=AUC_THRESHOLD, seed=SEED, genes=gene_names)
+        dt_csr = time.perf_counter() - t0
+        ref_api = out[:n_api].cpu().numpy()      # (the plans differ in the order max_auc's weights are summed: last-bit differences)
+        same_api = bool(np.allclose(got_api.values, ref_api, rtol=1e-12, atol=0))
+        n_df = int(min(n_api, args.api_frame_cells))
+        frame = pd.DataFrame(csr[:n_df].toarray(), index=["c%d" % i for i in range(n_df)], columns=gene_names)
+        api_aucell(frame.iloc[:256], sigs, auc_threshold=AUC_THRESHOLD, seed=SEED)
+        t0 = time.perf_counter()
+        got_df = api_aucell(frame, sigs, auc_threshold=AUC_THRESHOLD, seed=SEED)
+        dt_df = time.perf_counter() - t0
+        same_df = bool(np.allclose(got_df.values, ref_api[:n_df], rtol=1e-12, atol=0))
+        e2e_api = {"aucell_scipy_csr": {"value": n_api / dt_csr, "unit": "cells/s", "cells": n_api, "seconds": dt_csr,
+                                        "matches_device_path_1e-12": same_api,
+                                        "what": "pyscenic_b200.aucell.aucell(scipy.sparse.csr_matrix, signatures, genes=...) from "
+                                                "pageable numpy arrays to the returned DataFrame, incl. regulon preparation"},
+                   "aucell_dataframe": {"value": n_df / dt_df, "unit": "cells/s", "cells": n_df, "seconds": dt_df,
+                                        "matches_device_path_1e-12": same_df,
+                                        "what": "aucell(float32 DataFrame [cells x genes], signatures) -> DataFrame"}}
+        del csr, frame, got_api, got_df
+
     # ---- strong scaling (N > 1): one matrix, cell-sharded, gathered over NCCL, verified ------------------------------
     sharded = None
     if world > 1 and w["kind"] == "csr" and not args.no_e2e:
@@ -444,6 +480,7 @@ def run_ours(args, rank, world, local_rank):
                            "to host memory; checked bit for bit against a single-GPU run",
                 "timer": sharded["timer"]},
             "e2e_weak": None if sharded is None else e2e,
+            "e2e_api": e2e_api,
             "sharded": sharded,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -475,6 +512,9 @@ def main():
     ap.add_argument("--unweighted", action="store_true", help="unit gene weights (the CLI default of the reference)")
     ap.add_argument("--sharded-cells", type=int, default=0, help="cells of the strong-scaling matrix at N > 1 (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the aucell(scipy_csr) / aucell(DataFrame) records")
+    ap.add_argument("--api-cells", type=int, default=300_000, help="cells of the aucell(scipy_csr) record")
+    ap.add_argument("--api-frame-cells", type=int, default=20_000, help="cells of the aucell(DataFrame) record")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

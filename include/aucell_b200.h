@@ -148,6 +148,10 @@ int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, cons
                         int64_t chunk_cells);
 int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
+/* Host-side check of what the CSR entry points require: 1 when every row's column indices are strictly increasing and
+ * inside [0, n_genes) (scipy's "canonical format": sorted, no duplicates), 0 when not, negative on bad arguments.  On
+ * host threads, at memory speed (scipy's own check is single-threaded); no GPU involved. */
+int aucell_csr_is_canonical(const int64_t* h_indptr, const int32_t* h_indices, int64_t n_cells, int64_t n_genes);
 
 /* ---- downstream of the AUC matrix ------------------------------------------------------------------- */
 /* Regulon specificity scores (replaces pyscenic.rss.regulon_specificity_scores, reference src/pyscenic/rss.py:8-33):

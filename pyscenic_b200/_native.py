@@ -55,6 +55,7 @@ EXPORTED_SYMBOLS = [
     "aucell_from_rankings_u32",
     "aucell_csr_f32_host",
     "aucell_dense_f32_host",
+    "aucell_csr_is_canonical",
     "aucell_b200_launch_count",
     "aucell_plan_path_stats",
     "aucell_plan_last_host_bytes",
@@ -252,6 +253,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_from_rankings_u32.restype = c_int
         lib.aucell_csr_f32_host.argtypes = [p, p, p, p, i64, p, p, i64]
         lib.aucell_csr_f32_host.restype = c_int
+        lib.aucell_csr_is_canonical.argtypes = [p, p, i64, i64]
+        lib.aucell_csr_is_canonical.restype = c_int
         lib.aucell_dense_f32_host.argtypes = [p, p, i64, i64, p, p, i64]
         lib.aucell_dense_f32_host.restype = c_int
         _lib = lib

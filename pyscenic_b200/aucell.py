@@ -217,19 +217,28 @@ def _canonical_csr(mtx):
     import scipy.sparse as sp
 
     csr = mtx if sp.isspmatrix_csr(mtx) else sp.csr_matrix(mtx)
-    if not csr.has_canonical_format:
+    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    # sorted, duplicate-free rows are what the kernels need; the library checks that on all host cores (scipy's own
+    # has_canonical_format is a single-threaded scan: 2.5 s for the 1.3 M-cell benchmark matrix)
+    ok = _native.load().aucell_csr_is_canonical(indptr.ctypes.data, indices.ctypes.data, csr.shape[0], csr.shape[1])
+    if ok < 0:
+        _native.check(ok)
+    if ok == 0:
         csr = csr.copy()
         csr.sum_duplicates()
+        indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
     data = csr.data
     if data.dtype != np.float32:
         d = _dense_values(data)
         data = d
-    return csr.indptr.astype(np.int64, copy=False), csr.indices.astype(np.int32, copy=False), data
+    return indptr, indices, data
 
 
 def _assemble(values: np.ndarray, cells, names: Sequence[str], normalize: bool, num_workers: int) -> pd.DataFrame:
-    aucs = pd.DataFrame(
-        data=values, index=pd.Index(data=cells, name="Cell"), columns=pd.Index(data=list(names), name="Regulon")
+    aucs = pd.DataFrame(                       # (values is this call's own array: no defensive copy -- 0.7 s per 400 MB)
+        data=values, index=pd.Index(data=cells, name="Cell"), columns=pd.Index(data=list(names), name="Regulon"), copy=False
     )
     if num_workers == 1:
         # serial branch of the reference (aucell.py:118-130): concat + unstack sorts both axes by label and

@@ -430,6 +430,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
         cudaFree(hs.buf);
         cudaFreeHost(hs.pin_idx);
         cudaFreeHost(hs.pin_codes);
+        cudaFreeHost(hs.pin_out);
         if (hs.idx_done) cudaEventDestroy(hs.idx_done);
     }
     delete p;
@@ -578,7 +579,8 @@ constexpr int kHostSlots = 4;
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Make sure the plan owns kHostSlots staging buffers of at least `bytes` each (and their streams).
-int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0, size_t pin_codes_bytes = 0) {
+int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0, size_t pin_codes_bytes = 0,
+                      size_t pin_out_bytes = 0) {
     if (p->host_slots.empty()) p->host_slots.resize(kHostSlots);
     for (auto& hs : p->host_slots) {
         if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
@@ -606,6 +608,15 @@ int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes =
             CK(cudaHostAlloc((void**)&hs.pin_codes, pin_codes_bytes, cudaHostAllocDefault));
             hs.pin_codes_bytes = pin_codes_bytes;
         }
+        if (hs.pin_out_bytes < pin_out_bytes) {
+            CK(cudaStreamSynchronize(hs.st));
+            cudaFreeHost(hs.pin_out);
+            hs.pin_out = nullptr;
+            hs.pin_out_bytes = 0;
+            CK(cudaHostAlloc((void**)&hs.pin_out, pin_out_bytes, cudaHostAllocDefault));
+            hs.pin_out_bytes = pin_out_bytes;
+        }
+        hs.out_nc = 0;
         if ((pin_idx_bytes || pin_codes_bytes) && !hs.idx_done) CK(cudaEventCreateWithFlags(&hs.idx_done, cudaEventDisableTiming));
         hs.idx_pending = false;
     }
@@ -830,6 +841,39 @@ bool encode_values(ValueDict& d, const float* src_f, uint8_t* dst, int64_t n, in
     }
 }
 
+// Is this host pointer ordinary pageable memory (numpy / scipy arrays) rather than page-locked?  Copies from and to
+// pageable memory go through the driver's own bounce buffer at a fraction of the link rate and block the caller.
+bool is_pageable(const void* ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy spread over host threads (one core streams ~10 GB/s; the link wants 50)
+void copy_bytes(void* dst, const void* src, size_t n, int threads) {
+    if (threads <= 1 || n < ((size_t)1 << 22)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+        if (b >= e) continue;
+        try {
+            pool.emplace_back([=]() { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+        } catch (...) {
+            memcpy((char*)dst + b, (const char*)src + b, e - b);
+        }
+    }
+    memcpy(dst, src, std::min(n, per));
+    for (auto& th : pool) th.join();
+}
+
 int host_threads() {
     const char* env = getenv("AUCELL_B200_HOST_THREADS");
     if (env && *env) return std::max(1, std::min(64, atoi(env)));
@@ -898,10 +942,29 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     int chunk_no = 0;                     // pipeline rate once the slots are full: entries enqueued per second
     int64_t rate_n = 0;
     std::chrono::steady_clock::time_point rate_t0;
-    const int n_threads = (idx16 || val8) ? host_threads() : 1;
-    int rc = ensure_host_slots(p, bytes, idx16_allowed ? sizeof(uint16_t) * (size_t)max_nnz : 0,
-                               val8 ? (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax : 0);
+    // Pageable caller (numpy / scipy arrays): nothing is copied straight out of or into its memory.  Inputs that are not
+    // narrowed anyway are copied into the pinned staging by host threads, the AUC blocks land in pinned memory and are
+    // copied out when their slot comes round again.
+    const bool in_pageable = max_nnz > 0 && (is_pageable(h_indices) || is_pageable(h_data));
+    const bool out_pageable = is_pageable(h_out_auc) || (h_out_nnz && is_pageable(h_out_nnz));
+    const int n_threads = (idx16 || val8 || in_pageable || out_pageable) ? host_threads() : 1;
+    const size_t out_block = sizeof(double) * (size_t)chunk_cells * R;
+    int rc = ensure_host_slots(p, bytes,
+                               in_pageable ? sizeof(int32_t) * (size_t)max_nnz : (idx16_allowed ? sizeof(uint16_t) * (size_t)max_nnz : 0),
+                               in_pageable ? sizeof(float) * (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax
+                                           : (val8 ? (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax : 0),
+                               out_pageable ? out_block + sizeof(int32_t) * (size_t)chunk_cells : 0);
     if (rc) return rc;
+    auto drain_out = [&](aucell_plan::HostSlot& s) -> cudaError_t {      // the slot's pending AUC block -> the caller's arrays
+        if (s.out_nc == 0) return cudaSuccess;
+        const cudaError_t e = cudaStreamSynchronize(s.st);
+        if (e == cudaSuccess) {
+            copy_bytes(h_out_auc + s.out_c0 * R, s.pin_out, sizeof(double) * (size_t)s.out_nc * R, n_threads);
+            if (h_out_nnz) memcpy(h_out_nnz + s.out_c0, s.pin_out + out_block, sizeof(int32_t) * (size_t)s.out_nc);
+        }
+        s.out_nc = 0;
+        return e;
+    };
     int k = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
@@ -917,12 +980,13 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         const int64_t nc = c1 - c0;
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
         bool chunk8 = false;
+        if (out_pageable) CKB(drain_out(s));
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
         CKB(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
         h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1);
         d2h_bytes += (int64_t)sizeof(double) * nc * R + (h_out_nnz ? (int64_t)sizeof(int32_t) * nc : 0);
         if (ne > 0) {
-            const bool staged = idx16 || val8;
+            const bool staged = idx16 || val8 || in_pageable;
             if (staged) {
                 if (s.idx_pending) CKB(cudaEventSynchronize(s.idx_done));      // staging buffers free again
                 s.idx_pending = false;
@@ -944,16 +1008,24 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
             if (idx16) {
                 CKB(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, s.st));
                 h2d_bytes += (int64_t)sizeof(uint16_t) * ne;
+            } else if (in_pageable) {
+                copy_bytes(s.pin_idx, h_indices + e0, sizeof(int32_t) * (size_t)ne, n_threads);
+                CKB(cudaMemcpyAsync(d_indices, s.pin_idx, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
+                h2d_bytes += (int64_t)sizeof(int32_t) * ne;
             } else {
                 CKB(cudaMemcpyAsync(d_indices, h_indices + e0, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, s.st));
                 h2d_bytes += (int64_t)sizeof(int32_t) * ne;
             }
             if (chunk8) {
-                uint32_t* const pin_lut = reinterpret_cast<uint32_t*>(s.pin_codes + max_nnz);
+                uint32_t* const pin_lut = reinterpret_cast<uint32_t*>(s.pin_codes + (in_pageable ? sizeof(float) : 1) * (size_t)max_nnz);
                 memcpy(pin_lut, dict->lut, sizeof(uint32_t) * ValueDict::kMax);
                 CKB(cudaMemcpyAsync(d_codes, s.pin_codes, (size_t)ne, cudaMemcpyHostToDevice, s.st));
                 CKB(cudaMemcpyAsync(d_lut, pin_lut, sizeof(uint32_t) * ValueDict::kMax, cudaMemcpyHostToDevice, s.st));
                 h2d_bytes += ne + (int64_t)sizeof(uint32_t) * ValueDict::kMax;
+            } else if (in_pageable) {
+                copy_bytes(s.pin_codes, h_data + e0, sizeof(float) * (size_t)ne, n_threads);
+                CKB(cudaMemcpyAsync(d_vals, s.pin_codes, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
+                h2d_bytes += (int64_t)sizeof(float) * ne;
             } else {
                 CKB(cudaMemcpyAsync(d_vals, h_data + e0, sizeof(float) * ne, cudaMemcpyHostToDevice, s.st));
                 h2d_bytes += (int64_t)sizeof(float) * ne;
@@ -980,7 +1052,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         // (PCIe 5 x16 sustains ~50 GB/s: 0.10 ns per entry at 5 bytes, 0.12 at 6, 0.154 at 8).  Measured over three
         // chunks per format, the call steps down: both narrowings (3 bytes per entry, the host touches 11) -> byte codes
         // only (5, touches 5: the indices go up by DMA as they are) -> uint16 indices only (6, touches 6) -> as is (8).
-        if (narrow_chunks == 3 && narrow_n > (1 << 22)) {
+        // (a pageable caller's arrays are copied by the host in every format: the smallest upload stays)
+        if (!in_pageable && narrow_chunks == 3 && narrow_n > (1 << 22)) {
             const double t = narrow_ns / (double)narrow_n;
             bool changed = false;
             if (val8 && idx16) {
@@ -998,20 +1071,29 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         ++chunk_no;
         if (chunk_no == kHostSlots) rate_t0 = std::chrono::steady_clock::now();
         if (chunk_no > kHostSlots) rate_n += ne;
-        if (idx16 && !idx16_forced && !val8 && chunk_no == 3 * kHostSlots && rate_n > (1 << 24)) {
+        if (idx16 && !idx16_forced && !val8 && !in_pageable && chunk_no == 3 * kHostSlots && rate_n > (1 << 24)) {
             const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - rate_t0).count();
             if (ns > (double)rate_n / 4.5) idx16 = false;        // < 4.5 G entries/s
         }
-        CKB(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
-        if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        if (out_pageable) {
+            CKB(cudaMemcpyAsync(s.pin_out, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+            if (h_out_nnz) CKB(cudaMemcpyAsync(s.pin_out + out_block, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+            s.out_c0 = c0;
+            s.out_nc = nc;
+        } else {
+            CKB(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
+            if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
+        }
     }
     for (auto& s : p->host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+        if (rc == AUCELL_OK && out_pageable) drain_out(s);
+        s.out_nc = 0;
     }
     p->last_h2d_bytes = h2d_bytes;
     p->last_d2h_bytes = d2h_bytes;
-    if (rc == AUCELL_OK && total_nnz > (1 << 24)) {       // (a small call measures nothing)
+    if (rc == AUCELL_OK && total_nnz > (1 << 24) && !in_pageable) {       // (a small call measures nothing)
         p->hint_idx16 = idx16 || !idx16_allowed;
         p->hint_val8 = val8 || !val8_allowed;
     }
@@ -1021,6 +1103,40 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
                 narrow_ns > 0 ? (double)narrow_n / narrow_ns : 0.0, n_threads, (int)idx16, (int)val8, h2d_bytes * 1e-9,
                 d2h_bytes * 1e-9);
     return rc;
+}
+
+int aucell_csr_is_canonical(const int64_t* h_indptr, const int32_t* h_indices, int64_t n_cells, int64_t n_genes) {
+    if (!h_indptr || n_cells < 0) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    if (n_cells == 0) return 1;
+    if (!h_indices && h_indptr[n_cells] > h_indptr[0]) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    const int threads = std::max(1, std::min(host_threads(), (int)std::min<int64_t>(n_cells, 64)));
+    std::vector<int> bad((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t r0 = n_cells * t / threads, r1 = n_cells * (t + 1) / threads;
+        int b = 0;
+        for (int64_t r = r0; r < r1 && !b; ++r) {
+            const int64_t s = h_indptr[r], e = h_indptr[r + 1];
+            if (e < s) { b = 1; break; }
+            if (e == s) continue;
+            int32_t prev = h_indices[s];
+            int ok = prev >= 0 ? 1 : 0;
+            for (int64_t i = s + 1; i < e; ++i) {          // branch-free inner loop: the scan is memory bound
+                const int32_t c = h_indices[i];
+                ok &= (c > prev) ? 1 : 0;
+                prev = c;
+            }
+            if (!ok || (int64_t)prev >= n_genes) b = 1;
+        }
+        bad[(size_t)t] = b;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        try { pool.emplace_back(work, t); } catch (...) { work(t); }
+    }
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int b : bad) if (b) return 0;
+    return 1;
 }
 
 int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n_cells, int64_t row_stride,

@@ -114,6 +114,9 @@ struct aucell_plan {
         size_t pin_bytes = 0;
         uint8_t* pin_codes = nullptr;  // pinned host staging of a chunk's values as one-byte codes, then the 1 KB table
         size_t pin_codes_bytes = 0;
+        char* pin_out = nullptr;       // pageable callers: pinned landing zone of a chunk's AUC block (+ nnz), copied out
+        size_t pin_out_bytes = 0;      // by host threads when the slot comes round again
+        int64_t out_c0 = 0, out_nc = 0;   // the chunk waiting in pin_out (out_nc == 0: none)
         cudaEvent_t idx_done = nullptr;   // the upload out of pin_idx has finished
         bool idx_pending = false;
     };
