@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 3   /* 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -148,6 +148,10 @@ int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, cons
                         int64_t chunk_cells);
 int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
+/* The host-buffer calls keep their staging (four chunk slots per device: a stream, a device buffer, page-locked host
+ * buffers -- a few hundred MB) for the life of the process, because a plan is made per aucell() call and page-locking
+ * costs more than ranking 300,000 cells.  This frees it (device < 0: on every device). */
+int aucell_b200_release_staging(int device);
 /* Host-side check of what the CSR entry points require: 1 when every row's column indices are strictly increasing and
  * inside [0, n_genes) (scipy's "canonical format": sorted, no duplicates), 0 when not, negative on bad arguments.  On
  * host threads, at memory speed (scipy's own check is single-threaded); no GPU involved. */

@@ -425,15 +425,7 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_acc_scale);
     cudaFree(p->d_reg_max_auc);
     for (auto& kv : p->scratch) cudaFree(kv.second.first);
-    for (auto& hs : p->host_slots) {
-        if (hs.st) { cudaStreamSynchronize(hs.st); cudaStreamDestroy(hs.st); }
-        cudaFree(hs.buf);
-        cudaFreeHost(hs.pin_idx);
-        cudaFreeHost(hs.pin_codes);
-        cudaFreeHost(hs.pin_out);
-        if (hs.idx_done) cudaEventDestroy(hs.idx_done);
-    }
-    delete p;
+    delete p;          // (the staging buffers of the host-buffer calls belong to the device, not to the plan: staging_of)
     return AUCELL_OK;
 }
 
@@ -578,11 +570,39 @@ constexpr int kHostSlots = 4;
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// Make sure the plan owns kHostSlots staging buffers of at least `bytes` each (and their streams).
-int ensure_host_slots(const aucell_plan* p, size_t bytes, size_t pin_idx_bytes = 0, size_t pin_codes_bytes = 0,
-                      size_t pin_out_bytes = 0) {
-    if (p->host_slots.empty()) p->host_slots.resize(kHostSlots);
-    for (auto& hs : p->host_slots) {
+// Staging of the host-buffer calls: kHostSlots chunk slots (stream, device buffer, pinned host buffers) PER DEVICE,
+// kept for the life of the process (aucell_b200_release_staging frees them).  A plan is made per aucell() call, and
+// page-locking a few hundred MB costs more than ranking 300,000 cells: the buffers outlive the plans.  One host-buffer
+// call at a time per device (they would share the PCIe link anyway).
+struct DeviceStaging {
+    std::mutex mu;
+    std::vector<aucell_plan::HostSlot> slots;
+};
+std::mutex& staging_map_mu() { static std::mutex m; return m; }
+std::map<int, std::unique_ptr<DeviceStaging>>& staging_map() { static std::map<int, std::unique_ptr<DeviceStaging>> m; return m; }
+DeviceStaging& staging_of(int device) {
+    std::lock_guard<std::mutex> lk(staging_map_mu());
+    auto& e = staging_map()[device];
+    if (!e) e.reset(new DeviceStaging());
+    return *e;
+}
+void free_slots(std::vector<aucell_plan::HostSlot>& slots) {
+    for (auto& hs : slots) {
+        if (hs.st) { cudaStreamSynchronize(hs.st); cudaStreamDestroy(hs.st); }
+        cudaFree(hs.buf);
+        cudaFreeHost(hs.pin_idx);
+        cudaFreeHost(hs.pin_codes);
+        cudaFreeHost(hs.pin_out);
+        if (hs.idx_done) cudaEventDestroy(hs.idx_done);
+    }
+    slots.clear();
+}
+
+// Make sure the device's kHostSlots staging slots hold at least `bytes` each (and their streams).
+int ensure_host_slots(std::vector<aucell_plan::HostSlot>& slots, size_t bytes, size_t pin_idx_bytes = 0,
+                      size_t pin_codes_bytes = 0, size_t pin_out_bytes = 0) {
+    if (slots.empty()) slots.resize(kHostSlots);
+    for (auto& hs : slots) {
         if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
         if (hs.bytes < bytes) {
             CK(cudaStreamSynchronize(hs.st));
@@ -897,14 +917,19 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     if (!h_indptr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    DeviceStaging& staging = staging_of(p->device);
+    std::lock_guard<std::mutex> staging_lock(staging.mu);
     std::lock_guard<std::mutex> host_lock(p->host_mu);
+    std::vector<aucell_plan::HostSlot>& host_slots = staging.slots;
     const int64_t R = p->n_regulons;
     const int64_t total_nnz = h_indptr[n_cells] - h_indptr[0];
     if (total_nnz > 0 && (!h_indices || !h_data)) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     if (chunk_cells <= 0) {
-        // ~128 MB of (index, value) pairs per chunk
+        // ~128 MB of (index, value) pairs per chunk; 48 MB for a pageable caller, whose chunks pass through pinned
+        // buffers of the same size (page-locking them is the larger part of a first call on a few hundred thousand cells)
+        const double chunk_mb = (total_nnz > 0 && (is_pageable(h_indices) || is_pageable(h_data) || is_pageable(h_out_auc))) ? 48.0 : 128.0;
         const double per_cell = std::max<double>(1.0, (double)total_nnz / (double)n_cells);
-        chunk_cells = (int64_t)std::max<double>(1024.0, (128.0 * 1024 * 1024) / (8.0 * per_cell));
+        chunk_cells = (int64_t)std::max<double>(1024.0, (chunk_mb * 1024 * 1024) / (8.0 * per_cell));
     }
     chunk_cells = std::min(chunk_cells, n_cells);
     int64_t max_nnz = 0;
@@ -949,7 +974,7 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     const bool out_pageable = is_pageable(h_out_auc) || (h_out_nnz && is_pageable(h_out_nnz));
     const int n_threads = (idx16 || val8 || in_pageable || out_pageable) ? host_threads() : 1;
     const size_t out_block = sizeof(double) * (size_t)chunk_cells * R;
-    int rc = ensure_host_slots(p, bytes,
+    int rc = ensure_host_slots(host_slots, bytes,
                                in_pageable ? sizeof(int32_t) * (size_t)max_nnz : (idx16_allowed ? sizeof(uint16_t) * (size_t)max_nnz : 0),
                                in_pageable ? sizeof(float) * (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax
                                            : (val8 ? (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax : 0),
@@ -968,7 +993,7 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     int k = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
-        aucell_plan::HostSlot& s = p->host_slots[k];
+        aucell_plan::HostSlot& s = host_slots[k];
         int64_t* d_indptr = reinterpret_cast<int64_t*>(s.buf + o_indptr);
         int32_t* d_indices = reinterpret_cast<int32_t*>(s.buf + o_indices);
         float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
@@ -1085,7 +1110,7 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
             if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
         }
     }
-    for (auto& s : p->host_slots) {
+    for (auto& s : host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
         if (rc == AUCELL_OK && out_pageable) drain_out(s);
@@ -1139,6 +1164,24 @@ int aucell_csr_is_canonical(const int64_t* h_indptr, const int32_t* h_indices, i
     return 1;
 }
 
+int aucell_b200_release_staging(int device) {
+    std::vector<DeviceStaging*> which;
+    {
+        std::lock_guard<std::mutex> lk(staging_map_mu());
+        for (auto& kv : staging_map())
+            if (device < 0 || kv.first == device) which.push_back(kv.second.get());
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (DeviceStaging* st : which) {
+        std::lock_guard<std::mutex> lk(st->mu);
+        free_slots(st->slots);
+    }
+    cudaSetDevice(cur);
+    cudaGetLastError();
+    return AUCELL_OK;
+}
+
 int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells) {
     if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
@@ -1148,7 +1191,10 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
     if (!h_expr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    DeviceStaging& staging = staging_of(p->device);
+    std::lock_guard<std::mutex> staging_lock(staging.mu);
     std::lock_guard<std::mutex> host_lock(p->host_mu);
+    std::vector<aucell_plan::HostSlot>& host_slots = staging.slots;
     const int64_t R = p->n_regulons;
     if (chunk_cells <= 0)
         chunk_cells = std::max<int64_t>(256, (int64_t)(128.0 * 1024 * 1024 / (4.0 * (double)row_stride)));
@@ -1157,13 +1203,13 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
     const size_t o_auc = align256(o_vals + sizeof(float) * chunk_cells * row_stride);
     const size_t o_nnz = align256(o_auc + sizeof(double) * chunk_cells * R);
     const size_t bytes = align256(o_nnz + sizeof(int32_t) * chunk_cells);
-    int rc = ensure_host_slots(p, bytes);
+    int rc = ensure_host_slots(host_slots, bytes);
     if (rc) return rc;
     int k = 0;
     p->last_h2d_bytes = 0;
     p->last_d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
-        const aucell_plan::HostSlot& s = p->host_slots[k];
+        const aucell_plan::HostSlot& s = host_slots[k];
         float* d_vals = reinterpret_cast<float*>(s.buf + o_vals);
         double* d_auc = reinterpret_cast<double*>(s.buf + o_auc);
         int32_t* d_nnz = h_out_nnz ? reinterpret_cast<int32_t*>(s.buf + o_nnz) : nullptr;
@@ -1176,7 +1222,7 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
         CKB(cudaMemcpyAsync(h_out_auc + c0 * R, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
         if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
     }
-    for (auto& s : p->host_slots) {
+    for (auto& s : host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
     }

@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
     __shared__ int s_red_i[2][kFWarps];
     __shared__ KeyT s_red_k[2][kFWarps];
     __shared__ int s_flag[2];
+    __shared__ int s_str[2];              // the value bin that straddles the cutoff: index, base rank
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_genes = a.n_genes, cutoff = RANKS ? a.n_genes : a.rank_cutoff;
@@ -937,24 +938,57 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
 #pragma unroll
                 for (int j = 0; j < per; ++j) {
                     h1[b0 + j] = (uint32_t)run;
-                    if (run < cutoff && run + cnt[j] >= cutoff) s_flag[1] = run + cnt[j];   // at most one writer
+                    if (run < cutoff && run + cnt[j] >= cutoff) {      // at most one writer
+                        s_flag[1] = run + cnt[j];
+                        s_str[0] = b0 + j;
+                        s_str[1] = run;
+                    }
                     run += cnt[j];
                 }
                 if (tid == 0) h1[kNb1] = (uint32_t)n_gt;
             }
             __syncthreads();
             const int n_s = min(s_flag[1], n_gt);      // sentinel when all positives rank below the cutoff
+            int n_sub = n_s;                           // level-2 sub-buckets of the kept bins
+            int n_ent = n_s;                           // entries of the kept bins that come to registers
             if (!direct) {
-                // SELECT: bring the entries of the kept bins to registers (through the staging arrays)
-                if (n_s > kCapF) {
+                // SELECT: bring the entries of the kept bins to registers (through the staging arrays).
+                // When even the selection exceeds the capacity, the bin that straddles the cutoff is usually one huge
+                // tie class (the lowest expressed value of a deeply sequenced cell).  Of a tie class only the q =
+                // cutoff - base members at the smallest shuffled positions can rank below the cutoff, so only its
+                // first q + 8 sqrt(q) + 32 position sub-buckets are kept (positions are a random permutation: the
+                // count they hold is q + 8 sqrt(q) + 32 +- sqrt of that); the count is verified after the pass.
+                bool pruned = false;
+                uint32_t b_star = 0xFFFFFFFFu, c_star = 0u, s_star = 0u;
+                int q_star = 0;
+                if (n_s > kCapF && !RANKS && s_flag[1] != 0x7FFFFFFF) {
+                    b_star = (uint32_t)s_str[0];
+                    const int base_star = s_str[1];
+                    c_star = (uint32_t)(s_flag[1] - base_star);
+                    q_star = cutoff - base_star;
+                    const int keep_sub = q_star + 8 * (int)sqrtf((float)q_star) + 32;
+                    const int slack = 8 * (int)sqrtf((float)keep_sub) + 32;
+                    if (keep_sub < (int)c_star && base_star + keep_sub + slack <= kCapF) {
+                        pruned = true;
+                        s_star = (uint32_t)keep_sub;
+                        n_sub = base_star + keep_sub;
+                    }
+                }
+                if (n_sub > kCapF) {
                     general = true;           // even the selection does not fit: general path
                 } else {
                     stream_row(row, [&](bool ex, KeyT kk, int col) {
                         bool keep = false;
+                        PosT ps = (PosT)0;
                         if (ex && kk < KT::KEY_ZERO) {
                             const uint32_t b = (uint32_t)((kk - kmin) >> shift);
                             keep = (int)h1[b] < cutoff;
-                            if (keep && rep[b] != kk) atomicOr(&mixed[b >> 5], 1u << (b & 31));
+                            if (keep) {
+                                if (rep[b] != kk) atomicOr(&mixed[b >> 5], 1u << (b & 31));
+                                ps = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
+                                if (b == b_star)      // pruned tie class: the sub-bucket S4 will compute for it
+                                    keep = (uint32_t)(((unsigned long long)((unsigned)ps) * c_star * a.inv_ng) >> 32) < s_star;
+                            }
                         }
                         const unsigned mk = __ballot_sync(0xffffffffu, keep);
                         if (mk) {
@@ -964,18 +998,29 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             wbase = __shfl_sync(0xffffffffu, wbase, leader);
                             if (keep) {
                                 const int idx = wbase + __popc(mk & lanemask_lt());
-                                fk[idx] = kk;
-                                fp[idx] = __ldg(static_cast<const PosT*>(a.inv_perm) + col);
+                                if (idx < kCapF) {
+                                    fk[idx] = kk;
+                                    fp[idx] = ps;
+                                }
                             }
                         }
                     });
                     __syncthreads();
-                    nk = (n_s + kF - 1) / kF;
+                    if (pruned) {
+                        n_ent = s_cnt[1];
+                        // the pruning is only valid for a single-key bin that kept at least q members; the staging
+                        // arrays must have held everything
+                        if (((mixed[b_star >> 5] >> (b_star & 31)) & 1u) || n_ent > kCapF || n_ent - s_str[1] < q_star) {
+                            general = true;
+                            n_ent = 0;
+                        }
+                    }
+                    nk = (n_ent + kF - 1) / kF;
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         const int i = k * kF + tid;
-                        key[k] = (k < nk && i < n_s) ? fk[i] : KT::KEY_ZERO;
-                        pos[k] = (k < nk && i < n_s) ? fp[i] : (PosT)0;
+                        key[k] = (k < nk && i < n_ent) ? fk[i] : KT::KEY_ZERO;
+                        pos[k] = (k < nk && i < n_ent) ? fp[i] : (PosT)0;
                     }
                 }
                 __syncthreads();              // staging and rep are free again
@@ -983,7 +1028,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             if (!general) {
                 // S3: clear level-2 histogram (rep is dead: its last readers finished before the barriers above)
 #pragma unroll 1
-                for (int b = tid; b <= n_s; b += kF) h2[b] = 0u;
+                for (int b = tid; b <= n_sub; b += kF) h2[b] = 0u;
                 __syncthreads();
                 // S4: level-2 histogram
                 uint32_t sbs[kItems];     // (sub-bucket << 8) | arrival slot ; 0xFFFFFFFF = dropped
@@ -1022,8 +1067,8 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 } else {
                     // S5: exclusive scan of level-2 counts
                     {
-                        const int per = (n_s + kF - 1) / kF;
-                        const int b0 = tid * per, b1 = min(b0 + per, n_s);
+                        const int per = (n_sub + kF - 1) / kF;
+                        const int b0 = tid * per, b1 = min(b0 + per, n_sub);
                         int local = 0;
 #pragma unroll 1
                         for (int b = b0; b < b1; ++b) local += (int)h2[b];
@@ -1035,7 +1080,7 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                             h2[b] = (uint32_t)run;
                             run += c;
                         }
-                        if (tid == 0) h2[n_s] = (uint32_t)n_s;
+                        if (tid == 0) h2[n_sub] = (uint32_t)total;      // = entries in registers (n_sub unless pruned)
                     }
                     __syncthreads();
                     // S6: entries into sub-bucket order (sub-buckets starting at or beyond the cutoff are dropped)

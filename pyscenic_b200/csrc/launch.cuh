@@ -105,7 +105,7 @@ struct aucell_plan {
     uint16_t* d_xu = nullptr;
     unsigned long long* d_tie_stats = nullptr;   // [TIE_ST_N]
     void* d_reg_rec = nullptr;                   // [R] 32-byte epilogue records of aucell_tie_kernel
-    // staging buffers of the host-buffer pipeline (kept between calls; one host call at a time per plan)
+    // one staging slot of the host-buffer pipeline (the slots belong to the device and outlive the plans: aucell_b200.cu)
     struct HostSlot {
         cudaStream_t st = nullptr;
         char* buf = nullptr;       // one allocation: indptr | indices | values | auc | nnz
@@ -123,7 +123,6 @@ struct aucell_plan {
     mutable std::mutex host_mu;
     mutable int64_t last_h2d_bytes = 0, last_d2h_bytes = 0;   // what the last host-buffer call moved over PCIe
     mutable bool hint_idx16 = true, hint_val8 = true;         // upload format the last host-buffer call settled on
-    mutable std::vector<HostSlot> host_slots;
     // overflow scratch lists, one per stream that ever needed one
     mutable std::mutex mu;
     mutable std::map<std::pair<cudaStream_t, int>, std::pair<void*, size_t>> scratch;
@@ -168,7 +167,7 @@ inline int get_scratch(const aucell_plan* p, cudaStream_t st, int key_bytes, int
 
 // to-do list of the tie-class kernel: [0] counter (int32), list from byte 16 on; one per stream, grown on demand
 inline int get_todo(const aucell_plan* p, cudaStream_t st, int64_t n_cells, int32_t** todo, int32_t** todo_n) {
-    const size_t need = 16 + sizeof(int32_t) * (size_t)n_cells;
+    const size_t need = 16 + 2 * sizeof(int32_t) * (size_t)n_cells;      // two lists: general kernel, long rows
     std::lock_guard<std::mutex> lk(p->mu);
     auto& slot = p->scratch[{st, -1}];
     if (slot.second < need) {
@@ -179,7 +178,8 @@ inline int get_todo(const aucell_plan* p, cudaStream_t st, int64_t n_cells, int3
         if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(todo)", __LINE__);
         slot = {ptr, need};
     }
-    *todo_n = reinterpret_cast<int32_t*>(slot.first);          // [0] counter, [1..2] value range (tie_range_kernel)
+    *todo_n = reinterpret_cast<int32_t*>(slot.first);          // [0] counter, [1..2] value range (tie_range_kernel),
+                                                               // [3] counter of the long-row list (behind the first list)
     *todo = reinterpret_cast<int32_t*>((char*)slot.first + 16);
     return AUCELL_OK;
 }
@@ -213,6 +213,46 @@ inline TieLayout tie_layout(const aucell_plan* p, TieArgs& a, int cap) {
     return L;
 }
 
+// shared-memory carve-up of aucell_tie2_kernel (class bitmaps)
+inline TieLayout tie2_layout(const aucell_plan* p, TieArgs& a, int cap) {
+    const int ip_bytes = align16(((p->n_genes + 7) / 8) * 16);
+    a.nsw = (p->n_words + 3) / 4;
+    a.spt = (a.nsw + kTG - 1) / kTG;
+    int off = 0;
+    a.o_D = off; off = align16(off + ((kT2C + 1) * a.nsw + 8) * 16);        // + 32 spare words invalid lanes OR into
+    a.o_pre = off; off = align16(off + a.nsw * 16);
+    a.o_rep = off; off = align16(off + (kTieNB + 4) * 4);
+    a.o_code = off; off = align16(off + kTieNB);
+    a.o_fix = off; off = align16(off + kT2Fix * 8);
+    a.o_acc = off; off = align16(off + a.acc_words * 4);
+    a.o_misc = off; off = align16(off + kTieMiscWords * 4);
+    TieLayout L;
+    L.group_stride = off;
+    const int64_t room = p->smem_optin - ip_bytes;
+    L.groups = (int)std::max<int64_t>(0, std::min<int64_t>(kTieMaxGroups, room / off));
+    L.smem = ip_bytes + L.groups * off;
+    a.off_group0 = ip_bytes;
+    a.group_stride = off;
+    a.groups = L.groups;
+    a.cap = cap;
+    return L;
+}
+
+// which tie-class kernel: 1 = position-ordered list (aucell_tie_kernel), 2 = class bitmaps (aucell_tie2_kernel),
+// default: the first, with the rows beyond its capacity handed to the second
+inline int tie_version() {
+    const char* env = getenv("AUCELL_B200_TIE_KERNEL");
+    if (env && env[0] == '1' && env[1] == 0) return 1;
+    if (env && env[0] == '2' && env[1] == 0) return 2;
+    return 12;
+}
+
+inline int tie2_cap() {
+    const char* env = getenv("AUCELL_B200_TIE2_CAP");
+    int cap = env && *env ? atoi(env) : 16384;         // (16-bit prefixes: < 65536)
+    return std::max(256, std::min(32768, cap));
+}
+
 inline int tie_cap() {
     const char* env = getenv("AUCELL_B200_TIE_CAP");
     int cap = env && *env ? atoi(env) : kTieMaxCap;
@@ -228,36 +268,63 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     TieArgs a;
     memset(&a, 0, sizeof a);
     a.acc_words = p->weighted ? 2 * p->n_acc + 64 : p->n_acc + 32;       // + 32 dummy accumulators (empty table slots)
-    const TieLayout L = tie_layout(p, a, tie_cap());
-    if (L.groups < 1) return AUCELL_OK;            // does not fit: the caller runs aucell_fused_kernel on everything
+    const int version = tie_version();              // 1: aucell_tie_kernel, 2: aucell_tie2_kernel, 12: both (long rows to the second)
+    TieArgs a2;
+    memcpy(&a2, &a, sizeof a);
+    const TieLayout L1 = tie_layout(p, a, tie_cap());
+    const TieLayout L2 = tie2_layout(p, a2, tie2_cap());
+    // (the second kernel behind the first only when at least three of its cell groups fit an SM: with fewer -- more than
+    // ~40,000 genes -- aucell_fused_kernel ranks the long rows faster)
+    const bool use1 = version != 2 && L1.groups >= 1;
+    const bool use2 = version != 1 && L2.groups >= (version == 2 || !use1 ? 1 : 3);
+    if (!use1 && !use2) return AUCELL_OK;          // does not fit: the caller runs aucell_fused_kernel on everything
     int rc = get_todo(p, st, n_cells, todo, todo_n);
     if (rc) return rc;
-    CK(cudaMemsetAsync(*todo_n, 0, sizeof(int32_t), st));
-    a.indptr = indptr; a.indices = indices; a.data = data; a.lut = lut;
-    a.n_cells = n_cells; a.n_genes = p->n_genes; a.n_words = p->n_words;
-    a.wpt = ((p->n_words + kTG - 1) / kTG) | 1;          // words per thread in P2: odd, so that a warp's reads spread over the banks
-    a.cutoff = (int)p->rank_cutoff;
-    a.inv_perm = p->d_inv_perm16;
-    a.ell_w = p->d_ell_w; a.xw = p->d_xw; a.ell_u = p->d_ell_u; a.xu = p->d_xu;
-    a.L = p->tie_L;
-    a.n_regulons = p->n_regulons;
-    a.acc_first = p->d_acc_first; a.acc_parts = p->d_acc_parts; a.acc_scale = p->d_acc_scale;
-    a.reg_rec = p->d_reg_rec;
-    a.range = reinterpret_cast<const uint32_t*>(*todo_n) + 1;
-    a.max_auc = p->d_reg_max_auc;
-    a.out_auc = out_auc; a.out_nnz = out_nnz;
-    a.todo = *todo; a.todo_n = *todo_n;
-    a.stats = p->d_tie_stats;
-    const int grid = (int)std::min<int64_t>(p->sm_count, (n_cells + L.groups - 1) / L.groups);
+    CK(cudaMemsetAsync(*todo_n, 0, 4 * sizeof(int32_t), st));
+    for (TieArgs* x : {&a, &a2}) {
+        x->indptr = indptr; x->indices = indices; x->data = data; x->lut = lut;
+        x->n_cells = n_cells; x->n_genes = p->n_genes; x->n_words = p->n_words;
+        x->wpt = ((p->n_words + kTG - 1) / kTG) | 1;      // words per thread in P2: odd, so that a warp's reads spread over the banks
+        x->cutoff = (int)p->rank_cutoff;
+        x->inv_perm = p->d_inv_perm16;
+        x->ell_w = p->d_ell_w; x->xw = p->d_xw; x->ell_u = p->d_ell_u; x->xu = p->d_xu;
+        x->L = p->tie_L;
+        x->n_regulons = p->n_regulons;
+        x->acc_first = p->d_acc_first; x->acc_parts = p->d_acc_parts; x->acc_scale = p->d_acc_scale;
+        x->reg_rec = p->d_reg_rec;
+        x->range = reinterpret_cast<const uint32_t*>(*todo_n) + 1;
+        x->max_auc = p->d_reg_max_auc;
+        x->out_auc = out_auc; x->out_nnz = out_nnz;
+        x->todo = *todo; x->todo_n = *todo_n;
+        x->stats = p->d_tie_stats;
+    }
+    if (use1 && use2) {                            // rows beyond the first kernel's cap: a list for the second
+        a.long_list = *todo + n_cells;
+        a.long_n = *todo_n + 3;
+        a.long_cap = a2.cap;
+        a2.in_list = a.long_list;
+        a2.in_n = a.long_n;
+    }
     tie_range_kernel<IN><<<1, 1024, 0, st>>>(indptr, n_cells, data, lut, reinterpret_cast<uint32_t*>(*todo_n) + 1);
     launch_counter().fetch_add(1);
-#define LAUNCH_TIE(UNIT)                                                                          \
+#define LAUNCH_TIE(KERNEL, ARGS, LAY, WORK)                                                       \
     do {                                                                                          \
-        auto k = aucell_tie_kernel<IN, UNIT>;                                                     \
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));         \
-        k<<<grid, kTG * L.groups, L.smem, st>>>(a);                                               \
+        auto k = KERNEL;                                                                          \
+        const int grid = (int)std::min<int64_t>(p->sm_count, ((WORK) + LAY.groups - 1) / LAY.groups); \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, LAY.smem));       \
+        k<<<grid, kTG * LAY.groups, LAY.smem, st>>>(ARGS);                                        \
+        launch_counter().fetch_add(1);                                                            \
     } while (0)
-    if (p->weighted) LAUNCH_TIE(false); else LAUNCH_TIE(true);
+    if (use1) {
+        if (p->weighted) LAUNCH_TIE((aucell_tie_kernel<IN, false>), a, L1, n_cells);
+        else LAUNCH_TIE((aucell_tie_kernel<IN, true>), a, L1, n_cells);
+    }
+    if (use2) {
+        // (behind the first kernel the number of long rows is only known on the device: a full grid walks the list)
+        const int64_t work2 = n_cells;
+        if (p->weighted) LAUNCH_TIE((aucell_tie2_kernel<IN, false>), a2, L2, work2);
+        else LAUNCH_TIE((aucell_tie2_kernel<IN, true>), a2, L2, work2);
+    }
 #undef LAUNCH_TIE
     launch_counter().fetch_add(1);
     CK(cudaGetLastError());

@@ -86,12 +86,19 @@ struct TieArgs {
     int32_t* out_nnz;
     int32_t* todo;                      // cells left to aucell_fused_kernel
     int32_t* todo_n;
+    int32_t* long_list;                 // aucell_tie_kernel: rows longer than its cap (up to long_cap entries) go here,
+    int32_t* long_n;                    //   for aucell_tie2_kernel (nullptr: everything goes to `todo`)
+    int long_cap;
+    const int32_t* in_list;             // aucell_tie2_kernel: the cells to rank (nullptr: all n_cells)
+    const int32_t* in_n;
     unsigned long long* stats;          // [TIE_ST_N]
     int cap;                            // stored entries a group can hold
     int groups;
     // dynamic shared memory: inv_perm at 0, then `groups` blocks of group_stride bytes at off_group0
     int off_group0, group_stride;
     int o_A, o_wpre, o_rep, o_code, o_bpp, o_bpc, o_cnt, o_fix, o_acc, o_misc;
+    // aucell_tie2_kernel (class bitmaps): nsw = superwords (4 bitmap words) per bitmap, spt = superwords per thread in P2
+    int nsw, spt, o_D, o_pre;
 };
 
 // named barrier of one cell group (the builtin is convergent: the compiler reconverges the warp before it)
@@ -215,6 +222,7 @@ __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_
 template <bool UNIT>
 __device__ __forceinline__ void tie_apply_full_warp(const TieArgs& a, uint32_t acc_s, unsigned pos, uint32_t m,
                                                     uint32_t maskL, uint32_t dummy) {
+    if (!__any_sync(0xffffffffu, m != 0u)) return;         // (warp-uniform) nobody has work
     const TieRow<UNIT> row = tie_load_row<UNIT>(a, pos);
     uint32_t start, cnt;
     const bool chain = tie_apply_direct<UNIT>(a, acc_s, row, m, maskL, dummy, start, cnt);
@@ -349,7 +357,11 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         const int64_t rb = __ldg(a.indptr + cell);
         const int64_t n64 = __ldg(a.indptr + cell + 1) - rb;
         if (n64 < 0 || n64 > (int64_t)cap) {
-            hand_over(cell, TIE_ST_LONG);
+            if (a.long_list != nullptr && n64 > 0 && n64 <= (int64_t)a.long_cap) {      // aucell_tie2_kernel takes it
+                if (gtid == 0) a.long_list[atomicAdd(a.long_n, 1)] = (int32_t)cell;
+            } else {
+                hand_over(cell, TIE_ST_LONG);
+            }
             continue;
         }
         const int n = (int)n64;
@@ -611,6 +623,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         // ---------------- P7: the tail (largest values): exact order by (value, position) -------------------------
 #pragma unroll 1
         for (int f0 = 0; f0 < n_tail; f0 += kTG) {         // (uniform trip counts: see tie_apply_chain_warp)
+            if (f0 + (gw << 5) >= n_tail) break;            // (warp-uniform) this warp has no tail entry
             const int f = f0 + gtid;
             const uint2 mine = f < n_tail ? fix[f] : make_uint2(0u, 0u);
             int r = 0;
@@ -620,7 +633,8 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                 r += (o.x > mine.x || (o.x == mine.x && o.y < mine.y)) ? 1 : 0;
             }
             const uint32_t m = (f < n_tail && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
-            tie_apply_full_warp<UNIT>(a, acc_s, mine.y, m, maskL, dummy);
+            // (idle lanes: distinct positions -- 32 lanes adding 0 to ONE accumulator would serialise 32-way)
+            tie_apply_full_warp<UNIT>(a, acc_s, f < n_tail ? mine.y : (unsigned)min(lane, n_genes - 1), m, maskL, dummy);
         }
         // ---------------- P8: zeros fill the ranks npos .. cutoff-1 in position order ------------------------------
         // the q_zero-th zero sits at a position below q_zero + npos = cutoff: every thread scans positions [0, cutoff)
@@ -689,6 +703,451 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             if (r9 < R) orow[r9] = (sum == 0.0 || fx < 0) ? 0.0 : q;
         }
         // no barrier: the next cell clears its working set and passes a group barrier before it touches anything else
+    }
+}
+
+// =====================================================================================================================
+// aucell_tie2_kernel -- the same job with one position bitmap PER VALUE CLASS instead of a position-ordered list:
+//   rank(g) = base[class] + #{genes of the same class at smaller shuffled positions}
+//           = base[class] + prefix[class][superword] + popcount(bitmap[class][superword] below the position).
+// No list in position order, no counting sort, no second placement pass: an entry sets one bit (P1) and later reads one
+// 128-bit superword of its class bitmap and one 16-bit prefix (P3); in between, one pass over the bitmaps builds the
+// prefixes of all classes at once (P2).  kT2C classes (the lowest distinct values of the cell) have a bitmap; every
+// value above them is the tail (<= kT2Fix entries, exact order by pairs).  Same accumulators, same regulon table,
+// same epilogue as aucell_tie_kernel: the outputs are bit-identical.
+//   P0  classes         rep[bin] = value bits over the cell's stored values; occupied bins -> class (descending value)
+//   P1  bitmaps         D[class][pos] = 1 (one atomicOr per entry); tail entries also go to the pair list
+//   P2  prefixes        per superword (128 positions): popcounts of the kT2C class words and of their union -> one
+//                       packed scan (8 x 16 bit) -> pre[superword][class]; D[0] becomes the union (occupancy)
+//   P3  rank + scatter  every entry: rank from its class bitmap, then its row of the regulon table (as P6 above)
+//   P7-P9               tail, zero fill, AUCs out: as above
+constexpr int kT2C = 7;                 // value classes with a bitmap (class 0: the tail; after P2: occupancy)
+constexpr int kT2Fix = 256;             // tail entries per cell
+
+// exclusive scan of four packed words over the kTG threads of a group; s_w: kTGW uint4
+__device__ __forceinline__ uint4 group_excl_scan4(uint4 v, uint4* s_w, int lane, int gw, int barid, uint4& incl_out) {
+    uint4 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t tx = __shfl_up_sync(0xffffffffu, incl.x, o), ty = __shfl_up_sync(0xffffffffu, incl.y, o);
+        const uint32_t tz = __shfl_up_sync(0xffffffffu, incl.z, o), tw = __shfl_up_sync(0xffffffffu, incl.w, o);
+        if (lane >= o) { incl.x += tx; incl.y += ty; incl.z += tz; incl.w += tw; }
+    }
+    if (lane == 31) s_w[gw] = incl;
+    group_bar(barid);
+    uint4 off = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < kTGW - 1; ++k) {
+        if (k < gw) {                                      // (warp-uniform)
+            const uint4 w = s_w[k];
+            off.x += w.x; off.y += w.y; off.z += w.z; off.w += w.w;
+        }
+    }
+    incl_out = make_uint4(off.x + incl.x, off.y + incl.y, off.z + incl.z, off.w + incl.w);
+    return make_uint4(incl_out.x - v.x, incl_out.y - v.y, incl_out.z - v.z, incl_out.w - v.w);
+}
+
+// set bits of a 128-bit superword below bit `sh` (0 <= sh < 128)
+__device__ __forceinline__ uint32_t popc_below(const uint4 q, int sh) {
+    // __funnelshift_lc(~0, 0, n): the n low bits set, n clamped to 32
+    const uint32_t m0 = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)sh);
+    const uint32_t m1 = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(sh - 32, 0));
+    const uint32_t m2 = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(sh - 64, 0));
+    const uint32_t m3 = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(sh - 96, 0));
+    return (uint32_t)(__popc(q.x & m0) + __popc(q.y & m1) + __popc(q.z & m2) + __popc(q.w & m3));
+}
+
+template <int IN, bool UNIT>
+__global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie2_kernel(const TieArgs a) {
+    using IdxT = typename IdxOf<IN>::type;
+    using VT = TieVal<IN>;
+    using RowT = TieRow<UNIT>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, grp = tid / kTG, gtid = tid % kTG, lane = tid & 31, gw = gtid >> 5;
+
+    uint16_t* const ip = reinterpret_cast<uint16_t*>(smem);
+    {
+        const int nv = (a.n_genes + 7) >> 3;
+        const uint4* const src = reinterpret_cast<const uint4*>(a.inv_perm);
+        for (int i = tid; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(ip)[i] = __ldg(src + i);
+    }
+    unsigned char* const gb = smem + a.off_group0 + grp * a.group_stride;
+    uint32_t* const D = reinterpret_cast<uint32_t*>(gb + a.o_D);          // [kT2C + 1][4 nsw] class bitmaps, then 32 spare words
+    uint4* const D4 = reinterpret_cast<uint4*>(D);
+    uint16_t* const pre = reinterpret_cast<uint16_t*>(gb + a.o_pre);      // [nsw][8] set bits before the superword, per class
+    uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + a.o_rep);      // [kTieNB + 4]; from P3 on: the warps' chain lists
+    uint8_t* const code_of = reinterpret_cast<uint8_t*>(gb + a.o_code);   // [kTieNB] class of the bin
+    uint2* const fix = reinterpret_cast<uint2*>(gb + a.o_fix);            // [kT2Fix] (value bits, pos) of the tail
+    uint32_t* const acc = reinterpret_cast<uint32_t*>(gb + a.o_acc);
+    uint32_t* const misc = reinterpret_cast<uint32_t*>(gb + a.o_misc);
+    constexpr int kMScanA = 0;                 // [kTGW] scan words of P0
+    constexpr int kMScan4 = kTGW;              // [kTGW] uint4 scan words of P2
+    constexpr int kMBase = 5 * kTGW;           // [8] first rank of class c (c >= 1)
+    constexpr int kMTail = 5 * kTGW + 8;       // tail count, mixed, bad, stored non-zero values (one uint4)
+    constexpr int kMMixed = kMTail + 1;
+    constexpr int kMBad = kMTail + 2;
+    constexpr int kMValid = kMTail + 3;
+    constexpr int kMChain = kMTail + 4;        // [kTGW] chain list lengths
+    constexpr int kMNpos = kMChain + kTGW;     // occupied positions
+    static_assert(kMNpos < kTieMiscWords && kTGW % 4 == 0 && (kMTail % 4) == 0, "misc layout");
+    for (int i = gtid; i < a.acc_words; i += kTG) acc[i] = 0u;
+    if (gtid < kTGW) misc[kMChain + gtid] = 0u;
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    uint2* const chain_list = reinterpret_cast<uint2*>(rep) + gw * kTieChainCap;
+    __syncthreads();
+
+    const int barid = 1 + grp;
+    const int n_genes = a.n_genes, cutoff = a.cutoff, R = a.n_regulons, cap = a.cap, nsw = a.nsw;
+    const int dummy_word = (kT2C + 1) * 4 * nsw + lane;            // one spare word per lane behind the bitmaps
+    const uint32_t maskL = UNIT ? 0u : ((1u << a.L) - 1u);
+    const uint32_t dummy = UNIT ? (uint32_t)(a.acc_words - 32 + lane) : (uint32_t)(a.acc_words - 64 + 2 * lane) * 4u;
+    const uint32_t gmax = __ldg(a.range + 1);
+    const int shift = max(0, (32 - __clz((int)(gmax - __ldg(a.range)))) - kTieNBLog);
+    int seen = 0, handed = 0;
+
+    auto hand_over = [&](int64_t cell, int why) {
+        if (gtid == 0) {
+            const int k = atomicAdd(a.todo_n, 1);
+            a.todo[k] = (int32_t)cell;
+            if (a.stats != nullptr) atomicAdd(a.stats + why, 1ull);
+        }
+        ++handed;
+    };
+    auto bin_of = [&](uint32_t u) -> uint32_t {
+        const int d = max((int)(gmax - u), 0);
+        return min((uint32_t)d >> shift, (uint32_t)(kTieNB - 1));
+    };
+    // one item of the scatter: the direct slots now, a chained continuation onto the warp's list
+    auto scatter_item = [&](const RowT& row, uint32_t m) {
+        uint32_t start, cntc;
+        const bool chain = tie_apply_direct<UNIT>(a, acc_s, row, m, maskL, dummy, start, cntc);
+        if (chain) {
+            const uint32_t at = atomicAdd(&misc[kMChain + gw], 1u);
+            if (at < (uint32_t)kTieChainCap) {
+                chain_list[at] = make_uint2(start, (cntc << 16) | m);
+            } else {                                // list full (never seen): apply it here, lane by lane
+                if constexpr (UNIT) {
+                    cntc = __ldg(a.xu + start);
+                    for (uint32_t q = 1; q <= cntc; ++q) tie_slot_u(acc_s, __ldg(a.xu + start + q), m);
+                } else {
+                    for (uint32_t q = 0; q < cntc; ++q) {
+                        const uint2 sl = __ldg(a.xw + start + q);
+                        tie_slot_w(acc_s, sl.x, sl.y, m, a.L, maskL);
+                    }
+                }
+            }
+        }
+    };
+
+    const int64_t n_work = a.in_list != nullptr ? (int64_t)__ldg(a.in_n) : a.n_cells;
+    for (int64_t wi = (int64_t)blockIdx.x * a.groups + grp; wi < n_work; wi += (int64_t)gridDim.x * a.groups) {
+        const int64_t cell = a.in_list != nullptr ? (int64_t)__ldg(a.in_list + wi) : wi;
+        if (seen >= 16 && handed * 8 >= seen * 7) {        // data this kernel does not suit: stop looking
+            hand_over(cell, TIE_ST_SKIPPED);
+            continue;
+        }
+        ++seen;
+        const int64_t rb = __ldg(a.indptr + cell);
+        const int64_t n64 = __ldg(a.indptr + cell + 1) - rb;
+        if (n64 < 0 || n64 > (int64_t)cap) {
+            hand_over(cell, TIE_ST_LONG);
+            continue;
+        }
+        const int n = (int)n64;
+        const int iters = (n + kTieU * kTG - 1) / (kTieU * kTG);
+        const IdxT* const cols = reinterpret_cast<const IdxT*>(a.indices) + rb;
+        const typename VT::type* const vals = reinterpret_cast<const typename VT::type*>(a.data) + rb;
+
+        // ---------------- clear ----------------------------------------------------------------------------------
+        {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int nD4 = (kT2C + 1) * nsw + 8;
+            for (int i = gtid; i < nD4; i += kTG) D4[i] = z;
+#pragma unroll
+            for (int i = gtid; i < kTieNB / 4; i += kTG) reinterpret_cast<uint4*>(rep)[i] = z;
+            if (gtid == 0) *reinterpret_cast<uint4*>(misc + kMTail) = z;
+        }
+        group_bar(barid);
+
+        // ---------------- P0: one representative value per bin ----------------------------------------------------
+        {
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int base = it * (kTieU * kTG) + gtid;
+                uint32_t u[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) u[k] = base + k * kTG < n ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) rep[(u[k] << 1) != 0u ? bin_of(u[k]) : (uint32_t)kTieNB] = u[k];
+            }
+        }
+        group_bar(barid);
+        // occupied bins -> classes: index among the occupied bins (descending value); the kT2C lowest values get a
+        // bitmap each, everything above them is class 0, the tail
+        {
+            constexpr int kBinsPT = kTieNB / kTG;
+            static_assert(kBinsPT == 2, "two bins per thread");
+            const uint2 q0 = reinterpret_cast<const uint2*>(rep)[gtid];
+            uint32_t occ = (q0.x ? 1u : 0u) | (q0.y ? 2u : 0u);
+            if (gtid == 0) occ &= ~1u;         // bin 0 also takes every value above the sampled range: always tail
+            uint32_t total;
+            const uint32_t excl = group_excl_scan((uint32_t)__popc(occ), misc + kMScanA, lane, gw, barid, total);
+            const int excess = max(0, (int)total - kT2C);
+            int code = (int)excl;
+            uint32_t packed = 0u;
+#pragma unroll
+            for (int k = 0; k < kBinsPT; ++k) {
+                const int cls = code < excess ? 0 : code - excess + 1;
+                packed |= ((occ >> k) & 1u) ? (uint32_t)cls << (8 * k) : 0u;
+                code += (occ >> k) & 1u;
+            }
+            reinterpret_cast<uint16_t*>(code_of)[gtid] = (uint16_t)packed;
+        }
+        group_bar(barid);
+
+        // ---------------- P1: class bitmaps; the tail list ---------------------------------------------------------
+        {
+            uint32_t bad = 0u, mixed = 0u;
+            int nnz = 0;
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int base = it * (kTieU * kTG) + gtid;
+                uint32_t u[kTieU];
+                unsigned col[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool in = base + k * kTG < n;
+                    u[k] = in ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
+                    col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
+                }
+                bool any_tail = false;
+                uint32_t cls_k[kTieU], pos_k[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool nz = (u[k] << 1) != 0u;                     // +0.0 / -0.0 are not entries
+                    const bool valid = nz && col[k] < (unsigned)n_genes;   // (an invalid column leaves the bit count short)
+                    bad |= (nz && u[k] > 0x7F800000u) ? 1u : 0u;           // negative or NaN: not for this kernel
+                    nnz += nz ? 1 : 0;
+                    const unsigned pos = ip[valid ? col[k] : 0u];
+                    const uint32_t bin = bin_of(u[k]);
+                    const uint32_t cls = valid ? (uint32_t)code_of[bin] : 0u;
+                    mixed |= (valid && cls != 0u && rep[bin] != u[k]) ? 1u : 0u;   // two values in one class bin
+                    atomicOr(&D[valid ? cls * (4u * (unsigned)nsw) + (pos >> 5) : (unsigned)dummy_word],
+                             valid ? (1u << (pos & 31)) : 0u);
+                    any_tail |= valid && cls == 0u;
+                    cls_k[k] = valid ? cls : 1u;
+                    pos_k[k] = pos;
+                }
+                if (__any_sync(0xffffffffu, any_tail)) {   // rare: the largest values, beyond the kT2C classes
+#pragma unroll
+                    for (int k = 0; k < kTieU; ++k) {
+                        if (cls_k[k] == 0u) {
+                            const uint32_t f = atomicAdd(&misc[kMTail], 1u);
+                            if (f < (uint32_t)kT2Fix) fix[f] = make_uint2(u[k], pos_k[k]);
+                        }
+                    }
+                }
+            }
+            nnz = __reduce_add_sync(0xffffffffu, nnz);
+            bad = __reduce_or_sync(0xffffffffu, bad | (mixed << 1));
+            if (lane == 0) {
+                atomicAdd(&misc[kMValid], (uint32_t)nnz);
+                if (bad & 1u) misc[kMBad] = 1u;
+                if (bad & 2u) misc[kMMixed] = 1u;
+            }
+        }
+        group_bar(barid);
+
+        // ---------------- P2: prefixes of all class bitmaps at once ------------------------------------------------
+        {
+            const int s0 = gtid * a.spt, s1 = min(s0 + a.spt, nsw);
+            uint4 sum = make_uint4(0u, 0u, 0u, 0u);        // packed: {all | c1 << 16, c2 | c3 << 16, c4 | c5 << 16, c6 | c7 << 16}
+            static_assert(kT2C == 7, "eight 16-bit counts in four words");
+            auto count_sw = [&](int s, uint4& orw) -> uint4 {
+                uint32_t c[kT2C + 1];
+                orw = D4[s];
+#pragma unroll
+                for (int k = 1; k <= kT2C; ++k) {
+                    const uint4 q = D4[k * nsw + s];
+                    c[k] = (uint32_t)(__popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w));
+                    orw.x |= q.x; orw.y |= q.y; orw.z |= q.z; orw.w |= q.w;
+                }
+                c[0] = (uint32_t)(__popc(orw.x) + __popc(orw.y) + __popc(orw.z) + __popc(orw.w));
+                return make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+            };
+#pragma unroll 1
+            for (int s = s0; s < s1; ++s) {
+                uint4 orw;
+                const uint4 c = count_sw(s, orw);
+                sum.x += c.x; sum.y += c.y; sum.z += c.z; sum.w += c.w;
+            }
+            uint4 incl;
+            uint4 run = group_excl_scan4(sum, reinterpret_cast<uint4*>(misc + kMScan4), lane, gw, barid, incl);
+#pragma unroll 1
+            for (int s = s0; s < s1; ++s) {
+                uint4 orw;
+                const uint4 c = count_sw(s, orw);
+                reinterpret_cast<uint4*>(pre)[s] = run;
+                D4[s] = orw;                               // class 0's bitmap becomes the occupancy bitmap
+                run.x += c.x; run.y += c.y; run.z += c.z; run.w += c.w;
+            }
+            if (gtid == kTG - 1) {                         // totals -> first rank of every class
+                const uint32_t n_all = incl.x & 0xFFFFu;
+                uint32_t sz[kT2C + 1] = {0u, incl.x >> 16, incl.y & 0xFFFFu, incl.y >> 16, incl.z & 0xFFFFu, incl.z >> 16,
+                                         incl.w & 0xFFFFu, incl.w >> 16};
+                uint32_t in_cls = 0u;
+#pragma unroll
+                for (int k = 1; k <= kT2C; ++k) in_cls += sz[k];
+                uint32_t b = n_all - in_cls;               // the tail ranks first
+                misc[kMBase] = 0u;
+#pragma unroll
+                for (int k = 1; k <= kT2C; ++k) {
+                    misc[kMBase + k] = b;
+                    b += sz[k];
+                }
+                misc[kMNpos] = n_all;
+            }
+        }
+        group_bar(barid);
+        const int npos = (int)misc[kMNpos];
+        const int n_tail = (int)misc[kMTail];
+        {
+            const bool bad = misc[kMBad] != 0u, mixed = misc[kMMixed] != 0u;
+            const bool dup = (int)misc[kMValid] != npos;   // a column stored twice, or a column index out of range
+            if (bad || dup || mixed || n_tail > kT2Fix) {
+                group_bar(barid);                          // the flags are cleared by the next cell: read them first
+                hand_over(cell, bad ? TIE_ST_BADVAL : dup ? TIE_ST_DUP : mixed ? TIE_ST_MIXED : TIE_ST_TAIL);
+                continue;
+            }
+        }
+
+        // ---------------- P3: rank from the class bitmap, scatter --------------------------------------------------
+        {
+#pragma unroll 1
+            for (int it = 0; it < iters; ++it) {
+                const int base = it * (kTieU * kTG) + gtid;
+                uint32_t u[kTieU];
+                unsigned col[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool in = base + k * kTG < n;
+                    u[k] = in ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
+                    col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
+                }
+                uint32_t m[kTieU];
+                unsigned ps[kTieU];
+#pragma unroll
+                for (int k = 0; k < kTieU; ++k) {
+                    const bool valid = (u[k] << 1) != 0u;  // (columns are in range: the bit count matched)
+                    const unsigned pos = ip[valid ? col[k] : 0u];
+                    const uint32_t cls = valid ? (uint32_t)code_of[bin_of(u[k])] : 0u;
+                    const unsigned sw = pos >> 7;
+                    const uint4 q = D4[cls * (unsigned)nsw + sw];
+                    const int r = (int)(misc[kMBase + cls] + (uint32_t)pre[sw * 8u + cls] + popc_below(q, (int)(pos & 127u)));
+                    m[k] = (cls != 0u && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
+                    ps[k] = pos;
+                }
+#pragma unroll
+                for (int k0 = 0; k0 < kTieU; k0 += kTieP6) {
+                    RowT row[kTieP6];
+#pragma unroll
+                    for (int k = 0; k < kTieP6; ++k)
+                        if (m[k0 + k]) row[k] = tie_load_row<UNIT>(a, ps[k0 + k]);
+#pragma unroll
+                    for (int k = 0; k < kTieP6; ++k)
+                        if (m[k0 + k]) scatter_item(row[k], m[k0 + k]);
+                }
+            }
+            // the warp's deferred chains, one per lane
+            __syncwarp();
+            const int n_list = min((int)misc[kMChain + gw], kTieChainCap);
+#pragma unroll 1
+            for (int base = 0; base < n_list; base += 32) {
+                const int e = base + lane;
+                const uint2 ent = e < n_list ? chain_list[e] : make_uint2(0u, 0u);
+                uint32_t cntc = ent.y >> 16;
+                if constexpr (UNIT) cntc = e < n_list ? __ldg(a.xu + ent.x) : 0u;
+                tie_apply_chain_warp<UNIT>(a, acc_s, ent.x, cntc, ent.y & 0xFFFFu, maskL);
+            }
+            __syncwarp();
+            if (lane == 0) misc[kMChain + gw] = 0u;
+        }
+        // ---------------- P7: the tail (largest values): exact order by (value, position) -------------------------
+#pragma unroll 1
+        for (int f0 = 0; f0 < n_tail; f0 += kTG) {
+            if (f0 + (gw << 5) >= n_tail) break;            // (warp-uniform) this warp has no tail entry
+            const int f = f0 + gtid;
+            const uint2 mine = f < n_tail ? fix[f] : make_uint2(0u, 0u);
+            int r = 0;
+#pragma unroll 4
+            for (int g = 0; g < n_tail; ++g) {
+                const uint2 o = fix[g];
+                r += (o.x > mine.x || (o.x == mine.x && o.y < mine.y)) ? 1 : 0;
+            }
+            const uint32_t m = (f < n_tail && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
+            // (idle lanes: distinct positions -- 32 lanes adding 0 to ONE accumulator would serialise 32-way)
+            tie_apply_full_warp<UNIT>(a, acc_s, f < n_tail ? mine.y : (unsigned)min(lane, n_genes - 1), m, maskL, dummy);
+        }
+        // ---------------- P8: zeros fill the ranks npos .. cutoff-1 in position order ------------------------------
+        const int q_zero = cutoff - npos;
+        if (q_zero > 0) {
+#pragma unroll 1
+            for (int p0 = 0; p0 < cutoff; p0 += kTG) {
+                const int p = min(p0 + gtid, n_genes - 1);
+                const unsigned sw = (unsigned)p >> 7;
+                const uint4 q = D4[sw];
+                const int z = p - (int)pre[sw * 8u] - (int)popc_below(q, p & 127);          // zeros before p
+                const uint32_t bw = (p & 64) ? ((p & 32) ? q.w : q.z) : ((p & 32) ? q.y : q.x);
+                const bool is_zero = p0 + gtid < cutoff && !((bw >> (p & 31)) & 1u) && z < q_zero;
+                tie_apply_full_warp<UNIT>(a, acc_s, (unsigned)p, is_zero ? (uint32_t)(q_zero - z) : 0u, maskL, dummy);
+            }
+        }
+        if (gtid == 0) {
+            if (a.out_nnz != nullptr) a.out_nnz[cell] = npos;
+            if (a.stats != nullptr) atomicAdd(a.stats + TIE_ST_FAST, 1ull);
+        }
+        // ---------------- P9: AUCs out, accumulators cleared (as aucell_tie_kernel) ---------------------------------
+        __syncwarp();
+        double* const orow = a.out_auc + cell * (int64_t)R;
+        const int passes9 = (R + kTG - 1) / kTG;
+        int r9 = gtid;
+        const uint4* const recs = reinterpret_cast<const uint4*>(a.reg_rec);
+        const uint4 rec_none = make_uint4(0u, 0u, 0u, 0u), rec_none2 = make_uint4(0u, 0x3FF00000u, 0xFFFFFFFFu, 0u);
+        uint4 ra_n = r9 < R ? __ldg(recs + 2 * r9) : rec_none;
+        uint4 rb_n = r9 < R ? __ldg(recs + 2 * r9 + 1) : rec_none2;
+        group_bar(barid);
+#pragma unroll 1
+        for (int it = 0; it < passes9; ++it, r9 += kTG) {
+            const uint4 ra = ra_n, rb = rb_n;
+            if (it + 1 < passes9) {
+                const int rn = r9 + kTG;
+                ra_n = rn < R ? __ldg(recs + 2 * rn) : rec_none;
+                rb_n = rn < R ? __ldg(recs + 2 * rn + 1) : rec_none2;
+            }
+            const int fx = (int)rb.z;
+            const int f = fx < 0 ? 0 : fx;
+            const double mx = __hiloint2double((int)rb.y, (int)rb.x);
+            double sum;
+            if constexpr (UNIT) {
+                sum = (double)acc[f];
+                if (fx >= 0) acc[f] = 0u;
+            } else {
+                const bool has2 = rb.w != 0u;
+                const int f2 = has2 ? f + 1 : ((a.acc_words - 64) >> 1) + lane;
+                uint2 lh = *reinterpret_cast<const uint2*>(acc + 2 * f);
+                uint2 l2 = *reinterpret_cast<const uint2*>(acc + 2 * f2);
+                if (fx >= 0) *reinterpret_cast<uint2*>(acc + 2 * f) = make_uint2(0u, 0u);
+                if (has2) *reinterpret_cast<uint2*>(acc + 2 * f2) = make_uint2(0u, 0u);
+                if (f & 16) lh = make_uint2(lh.y, lh.x);
+                if (f2 & 16) l2 = make_uint2(l2.y, l2.x);
+                const long long v0 = (long long)(((unsigned long long)lh.y << a.L) + (unsigned long long)lh.x);
+                const long long v1 = (long long)(((unsigned long long)l2.y << a.L) + (unsigned long long)l2.x);
+                sum = (double)v0 * __hiloint2double((int)ra.y, (int)ra.x);
+                sum += (double)v1 * __hiloint2double((int)ra.w, (int)ra.z);
+            }
+            const double q = __ddiv_rn(nonzero_numerator(sum), mx);
+            if (r9 < R) orow[r9] = (sum == 0.0 || fx < 0) ? 0.0 : q;
+        }
     }
 }
 

@@ -91,22 +91,47 @@ def prepare_regulons(columns, perm: Optional[np.ndarray], signatures: Sequence, 
     n_genes = len(labels)
     if perm is None:
         perm = np.arange(n_genes, dtype=np.int64)
-    # gene label -> shuffled positions holding that label (duplicate column names are all selected, like isin)
+    perm = np.asarray(perm, dtype=np.int64)
+    # gene label -> shuffled position(s) holding that label.  Labels are normally unique: one dict built at C speed;
+    # duplicate column names (all of them are selected, like isin) take the list-valued dict.
     shuffled_labels = labels[perm]
-    pos_of = {}
-    for j, g in enumerate(shuffled_labels):
-        pos_of.setdefault(g, []).append(j)
+    pos_of = dict(zip(shuffled_labels.tolist(), range(n_genes)))
+    multi = None
+    if len(pos_of) != n_genes:
+        multi = {}
+        for j, g in enumerate(shuffled_labels):
+            multi.setdefault(g, []).append(j)
 
     names, indptr, cols_l, w_l, max_auc, valid = [], [0], [], [], [], []
     rank_cutoff = None
-    for sig in signatures:
-        if noweights:
-            sig = sig.noweights()
+    # one pass over all (gene, weight) pairs of all signatures: label -> position at C speed, one array conversion
+    sigs = [sig.noweights() if noweights else sig for sig in signatures]
+    keys, vals, bounds = [], [], [0]
+    for sig in sigs:
+        g2w = getattr(sig, "gene2weight", None)
+        if hasattr(g2w, "keys"):
+            keys.extend(g2w.keys())
+            vals.extend(g2w.values())
+        else:
+            gs = list(sig.genes)
+            keys.extend(gs)
+            vals.extend(sig[g] for g in gs)
+        bounds.append(len(keys))
+    all_w = np.asarray(vals, dtype=np.float64)
+    if multi is None:
+        all_pos = np.asarray(list(map(pos_of.get, keys, [-1] * len(keys))), dtype=np.int64)
+    for k, sig in enumerate(sigs):
         names.append(sig.name)
-        sel = []
-        for g in sig.genes:
-            sel.extend(pos_of.get(g, ()))
-        sel.sort()  # column order of rnk_mtx.iloc[:, isin]
+        b0, b1 = bounds[k], bounds[k + 1]
+        if multi is None:
+            ps = all_pos[b0:b1]
+            present = ps >= 0
+            sel = ps[present]
+            w = all_w[b0:b1][present]
+        else:
+            hit = [(j, wt) for g, wt in zip(keys[b0:b1], vals[b0:b1]) for j in multi.get(g, ())]
+            sel = np.asarray([h[0] for h in hit], dtype=np.int64)
+            w = np.asarray([h[1] for h in hit], dtype=np.float64)
         n_sel = len(sel)
         if n_sel == 0 or (float(n_sel) / float(len(sig))) < 0.80:
             LOGGER.warning(
@@ -118,7 +143,9 @@ def prepare_regulons(columns, perm: Optional[np.ndarray], signatures: Sequence, 
             continue
         if rank_cutoff is None:
             rank_cutoff = derive_rank_cutoff(auc_threshold, n_genes)
-        w = np.asarray([sig[g] for g in shuffled_labels[sel]], dtype=np.float64)
+        order = np.argsort(sel, kind="stable")             # column order of rnk_mtx.iloc[:, isin] (positions are unique)
+        sel = sel[order]
+        w = np.ascontiguousarray(w[order])
         y_max = w.sum()
         m = float((rank_cutoff + 1) * y_max)
         assert m > 0

@@ -18,8 +18,10 @@ for weighted in (True, False):
     dev = torch.device("cuda", 0)
     indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, mean_nnz, seed=1000, device=dev)
     res = {}
-    for fast in (True, False):
-        avail = plan.set_fast_path(fast)
+    for fast in (2, 1, False):                      # tie-class kernel version (AUCELL_B200_TIE_KERNEL), or the general kernel
+        if fast:
+            os.environ["AUCELL_B200_TIE_KERNEL"] = str(fast)
+        avail = plan.set_fast_path(bool(fast))
         out = torch.full((n_cells, R), -1.0, dtype=torch.float64, device=dev)
         nnz = torch.full((n_cells,), -1, dtype=torch.int32, device=dev)
         for _ in range(2):
@@ -35,12 +37,13 @@ for weighted in (True, False):
         print(json.dumps({"weighted": weighted, "fast": fast, "available": avail, "ms": ms,
                           "Mcells_per_s": n_cells / ms / 1e3, "fast_stats": plan.fast_stats(),
                           "path_stats": plan.path_stats()}), flush=True)
-    same = torch.equal(res[True][0], res[False][0]); same_nnz = torch.equal(res[True][1], res[False][1])
-    diff = (res[True][0] - res[False][0]).abs().max().item()
-    print("weighted", weighted, "identical:", same, "nnz identical:", same_nnz, "max abs diff", diff, flush=True)
-    if not same:
-        bad = (res[True][0] != res[False][0]).any(dim=1).nonzero().flatten()
-        print("bad cells:", bad.numel(), bad[:10].tolist())
-        c = int(bad[0]); cols = (res[True][0][c] != res[False][0][c]).nonzero().flatten()[:5].tolist()
-        print("cell", c, "nnz", int(indptr[c+1]-indptr[c]), "cols", cols, res[True][0][c, cols].tolist(), res[False][0][c, cols].tolist())
+    for v in (2, 1):
+        same = torch.equal(res[v][0], res[False][0]); same_nnz = torch.equal(res[v][1], res[False][1])
+        diff = (res[v][0] - res[False][0]).abs().max().item()
+        print("weighted", weighted, "kernel", v, "identical:", same, "nnz identical:", same_nnz, "max abs diff", diff, flush=True)
+        if not same:
+            bad = (res[v][0] != res[False][0]).any(dim=1).nonzero().flatten()
+            print("bad cells:", bad.numel(), bad[:10].tolist())
+            c = int(bad[0]); cols = (res[v][0][c] != res[False][0][c]).nonzero().flatten()[:5].tolist()
+            print("cell", c, "nnz", int(indptr[c+1]-indptr[c]), "cols", cols, res[v][0][c, cols].tolist(), res[False][0][c, cols].tolist())
     plan.close()

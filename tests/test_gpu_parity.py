@@ -605,12 +605,19 @@ def _mixed_bag_matrix(rs, n_genes):
     return X, m
 
 
+@pytest.mark.parametrize("tie_kernel", ["12", "1", "2"])
 @pytest.mark.parametrize("unweighted", [False, True])
 @pytest.mark.parametrize("n_genes", [5000, 20011])
-def test_tie_class_kernel_equals_general_kernel_bit_for_bit(unweighted, n_genes):
-    """The two kernels behind aucell_csr_f32 / aucell_csr16_f32 add the same integers: switching the tie-class kernel
-    off must not change one bit, whatever mixture of cells the matrix holds; and both match the oracle."""
+def test_tie_class_kernel_equals_general_kernel_bit_for_bit(unweighted, n_genes, tie_kernel, monkeypatch):
+    """The kernels behind aucell_csr_f32 / aucell_csr16_f32 add the same integers: switching the tie-class kernels
+    off must not change one bit, whatever mixture of cells the matrix holds; and all match the oracle.
+    tie_kernel: "1" aucell_tie_kernel alone, "2" aucell_tie2_kernel alone (capacity lowered so that it hands the long
+    row over), "12" the default -- the first kernel with the rows beyond its capacity handed to the second."""
     import torch
+
+    monkeypatch.setenv("AUCELL_B200_TIE_KERNEL", tie_kernel)
+    if tie_kernel == "2":
+        monkeypatch.setenv("AUCELL_B200_TIE2_CAP", "4096")
 
     rs = np.random.RandomState(11)
     X, m = _mixed_bag_matrix(rs, n_genes)
@@ -631,7 +638,8 @@ def test_tie_class_kernel_equals_general_kernel_bit_for_bit(unweighted, n_genes)
         nnz_g = torch.empty_like(nnz_f)
         general = plan.aucell_csr(indptr, indices, data, out_nnz=nnz_g)
         plan.set_fast_path(True)
-    assert fs["ranked"] > 0 and fs["handed_long_row"] > 0 and fs["handed_negative_or_nan"] > 0
+    assert fs["ranked"] > 0 and fs["handed_negative_or_nan"] > 0
+    assert (fs["handed_long_row"] > 0) == (tie_kernel != "12")
     assert fs["handed_mixed_bin"] + fs["handed_tail_overflow"] + fs["handed_skipped"] > 0
     assert fs["ranked"] + sum(v for k, v in fs.items() if k.startswith("handed")) == m.shape[0]
     assert torch.equal(fast, general) and torch.equal(fast16, general)
