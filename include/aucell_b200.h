@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -51,7 +51,8 @@ enum {
     AUCELL_ERR_CUDA = -2,      /* a CUDA runtime call or kernel failed                                 */
     AUCELL_ERR_NO_DEVICE = -3, /* no CUDA device / not an sm_100 device                                */
     AUCELL_ERR_UNSUPPORTED = -4, /* shape outside what the kernels support (see aucell_b200_limits)   */
-    AUCELL_ERR_NOMEM = -5
+    AUCELL_ERR_NOMEM = -5,
+    AUCELL_NOT_SPARSE = 1      /* aucell_dense_strided_host only: nothing computed, use another entry point     */
 };
 
 /* opaque: per-call constants of one AUCell job, resident on one device */
@@ -148,6 +149,15 @@ int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, cons
                         int64_t chunk_cells);
 int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
+/* A host matrix in dense storage as a pandas DataFrame holds it: float32 (is_f64 = 0) or float64 values, cell-major
+ * (gene_stride == 1, cell_stride >= n_genes) or gene-major (cell_stride == 1, gene_stride >= n_cells; strides in
+ * elements).  Expression matrices are mostly zeros: host threads squeeze them out in one pass at memory speed and the
+ * call continues as aucell_csr_f32_host -- a fraction of the bytes over PCIe, and the CSR kernels on the device.
+ * Returns AUCELL_NOT_SPARSE (1), with nothing computed, when more than 30 % of a sample of the entries are non-zero,
+ * when a float64 value does not survive the cast to float32 (a cast that changes values may create ties the input does
+ * not have), or when the plan has no tie-class kernel: the caller then uses aucell_dense_f32_host / device chunks. */
+int aucell_dense_strided_host(const aucell_plan_t* plan, const void* h_expr, int is_f64, int64_t n_cells,
+                              int64_t cell_stride, int64_t gene_stride, double* h_out_auc, int32_t* h_out_nnz);
 /* The host-buffer calls keep their staging (four chunk slots per device: a stream, a device buffer, page-locked host
  * buffers -- a few hundred MB) for the life of the process, because a plan is made per aucell() call and page-locking
  * costs more than ranking 300,000 cells.  This frees it (device < 0: on every device). */

@@ -187,6 +187,10 @@ def _device_chunks(values: np.ndarray, device: int, chunk_bytes: int = 256 << 20
 
 
 def _dense_auc_shard(plan: AUCellPlan, values: np.ndarray, out: np.ndarray, device: int) -> None:
+    # expression matrices are mostly zeros: the library squeezes them out on host threads, whatever the layout (a
+    # DataFrame block is gene-major) and float type, and ranks the rest through the CSR kernels
+    if plan.aucell_dense_strided_host(values, out):
+        return
     if values.dtype == np.float32 and values.flags.c_contiguous:
         out[:] = plan.aucell_dense_host(values)       # library streams the host buffer itself
         return

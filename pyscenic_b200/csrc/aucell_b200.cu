@@ -8,6 +8,7 @@
 #include <thread>
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
+#include <sys/mman.h>
 #endif
 
 using namespace aucell;
@@ -602,6 +603,8 @@ void free_slots(std::vector<aucell_plan::HostSlot>& slots) {
 int ensure_host_slots(std::vector<aucell_plan::HostSlot>& slots, size_t bytes, size_t pin_idx_bytes = 0,
                       size_t pin_codes_bytes = 0, size_t pin_out_bytes = 0) {
     if (slots.empty()) slots.resize(kHostSlots);
+    // grow with head-room: the next call's chunks are rarely the same size to the byte, and re-pinning costs ~0.1 s per GB
+    auto roomy = [](size_t want) { return want == 0 ? (size_t)0 : ((want + want / 4 + ((size_t)8 << 20)) & ~(((size_t)1 << 20) - 1)); };
     for (auto& hs : slots) {
         if (!hs.st) CK(cudaStreamCreateWithFlags(&hs.st, cudaStreamNonBlocking));
         if (hs.bytes < bytes) {
@@ -609,32 +612,32 @@ int ensure_host_slots(std::vector<aucell_plan::HostSlot>& slots, size_t bytes, s
             cudaFree(hs.buf);
             hs.buf = nullptr;
             hs.bytes = 0;
-            CK(cudaMalloc(&hs.buf, bytes));
-            hs.bytes = bytes;
+            CK(cudaMalloc(&hs.buf, roomy(bytes)));
+            hs.bytes = roomy(bytes);
         }
         if (hs.pin_bytes < pin_idx_bytes) {
             CK(cudaStreamSynchronize(hs.st));
             cudaFreeHost(hs.pin_idx);
             hs.pin_idx = nullptr;
             hs.pin_bytes = 0;
-            CK(cudaHostAlloc((void**)&hs.pin_idx, pin_idx_bytes, cudaHostAllocDefault));
-            hs.pin_bytes = pin_idx_bytes;
+            CK(cudaHostAlloc((void**)&hs.pin_idx, roomy(pin_idx_bytes), cudaHostAllocDefault));
+            hs.pin_bytes = roomy(pin_idx_bytes);
         }
         if (hs.pin_codes_bytes < pin_codes_bytes) {
             CK(cudaStreamSynchronize(hs.st));
             cudaFreeHost(hs.pin_codes);
             hs.pin_codes = nullptr;
             hs.pin_codes_bytes = 0;
-            CK(cudaHostAlloc((void**)&hs.pin_codes, pin_codes_bytes, cudaHostAllocDefault));
-            hs.pin_codes_bytes = pin_codes_bytes;
+            CK(cudaHostAlloc((void**)&hs.pin_codes, roomy(pin_codes_bytes), cudaHostAllocDefault));
+            hs.pin_codes_bytes = roomy(pin_codes_bytes);
         }
         if (hs.pin_out_bytes < pin_out_bytes) {
             CK(cudaStreamSynchronize(hs.st));
             cudaFreeHost(hs.pin_out);
             hs.pin_out = nullptr;
             hs.pin_out_bytes = 0;
-            CK(cudaHostAlloc((void**)&hs.pin_out, pin_out_bytes, cudaHostAllocDefault));
-            hs.pin_out_bytes = pin_out_bytes;
+            CK(cudaHostAlloc((void**)&hs.pin_out, roomy(pin_out_bytes), cudaHostAllocDefault));
+            hs.pin_out_bytes = roomy(pin_out_bytes);
         }
         hs.out_nc = 0;
         if ((pin_idx_bytes || pin_codes_bytes) && !hs.idx_done) CK(cudaEventCreateWithFlags(&hs.idx_done, cudaEventDisableTiming));
@@ -894,6 +897,280 @@ void copy_bytes(void* dst, const void* src, size_t n, int threads) {
     for (auto& th : pool) th.join();
 }
 
+// ---- dense host rows -> CSR on host threads --------------------------------------------------------------------------
+// A dense [cells x genes] float32 matrix of single-cell counts is ~93 % zeros: uploading it costs 4 bytes per GENE and
+// cell, ranking it through the CSR kernels 3..8 bytes per EXPRESSED gene.  The host threads therefore squeeze the zeros
+// out (one pass at memory speed, AVX2 compress through a permutation table) and the call continues as a CSR call.
+// +0.0 / -0.0 are dropped (they rank as zeros either way), NaN is kept.
+extern "C++" {
+template <typename T> struct RawBuf {          // uninitialised growable array (std::vector would zero-fill what is about to be written)
+    std::unique_ptr<T[]> p;
+    size_t cap = 0;
+    T* data() { return p.get(); }
+    size_t size() const { return cap; }
+    void grow(size_t n, size_t keep) {
+        if (n <= cap) return;
+        std::unique_ptr<T[]> q(new T[n]);
+        if (keep) memcpy(q.get(), p.get(), sizeof(T) * keep);
+        p.swap(q);
+        cap = n;
+    }
+};
+}  // extern "C++"
+struct CompactLut {
+    alignas(32) uint32_t perm[256][8];
+    alignas(16) uint16_t lane[256][8];
+    CompactLut() {
+        for (int m = 0; m < 256; ++m) {
+            int k = 0;
+            for (int b = 0; b < 8; ++b)
+                if (m & (1 << b)) { perm[m][k] = (uint32_t)b; lane[m][k] = (uint16_t)b; ++k; }
+            for (; k < 8; ++k) { perm[m][k] = 0; lane[m][k] = 0; }
+        }
+    }
+};
+const CompactLut& compact_lut() { static const CompactLut l; return l; }
+
+// non-zero entries of row[0..n) -> (idx, val), both with room for 8 entries past the result; returns their number
+int64_t compact_row_scalar(const float* row, int64_t j0, int64_t n, int32_t* idx, float* val) {
+    int64_t k = 0;
+    for (int64_t j = j0; j < n; ++j) {
+        const float v = row[j];
+        if (v != 0.0f) { idx[k] = (int32_t)j; val[k] = v; ++k; }       // (NaN != 0: kept)
+    }
+    return k;
+}
+#ifdef AUCELL_HAVE_AVX2_PATH
+__attribute__((target("avx2,popcnt"))) int64_t compact_row_avx2(const float* row, int64_t n, int32_t* idx, float* val) {
+    const CompactLut& L = compact_lut();
+    const __m256 zero = _mm256_setzero_ps();
+    int64_t k = 0, j = 0;
+    for (; j + 8 <= n; j += 8) {
+        const __m256 v = _mm256_loadu_ps(row + j);
+        const int m = _mm256_movemask_ps(_mm256_cmp_ps(v, zero, _CMP_NEQ_UQ));
+        if (m == 0) continue;
+        const __m256i pm = _mm256_load_si256(reinterpret_cast<const __m256i*>(L.perm[m]));
+        _mm256_storeu_ps(val + k, _mm256_permutevar8x32_ps(v, pm));
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(idx + k), _mm256_add_epi32(pm, _mm256_set1_epi32((int)j)));
+        k += __builtin_popcount((unsigned)m);
+    }
+    return k + compact_row_scalar(row, j, n, idx + k, val + k);
+}
+#endif
+int64_t compact_row(const float* row, int64_t n, int32_t* idx, float* val) {
+#ifdef AUCELL_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) return compact_row_avx2(row, n, idx, val);
+#endif
+    return compact_row_scalar(row, 0, n, idx, val);
+}
+
+constexpr int kNotCompacted = 1000;      // internal: the matrix is not sparse / not exact in float32; take another path
+
+extern "C++" {
+// value -> float32 when that is exact (a cast that changes a value may create ties the input does not have)
+inline bool to_f32_exact(float v, float& f) { f = v; return true; }
+inline bool to_f32_exact(double v, float& f) { f = (float)v; return (double)f == v || v != v; }
+template <typename T> inline bool is_zero_bits(const T* p);
+template <> inline bool is_zero_bits<float>(const float* p) { uint32_t u; memcpy(&u, p, 4); return (u << 1) == 0u; }
+template <> inline bool is_zero_bits<double>(const double* p) { uint64_t u; memcpy(&u, p, 8); return (u << 1) == 0ull; }
+
+// non-zero entries of one contiguous row; false: a value is not exact in float32
+template <typename T> bool compact_row_t(const T* row, int64_t n, int32_t* idx, float* val, int64_t& k_out);
+template <> bool compact_row_t<float>(const float* row, int64_t n, int32_t* idx, float* val, int64_t& k_out) {
+    k_out = compact_row(row, n, idx, val);
+    return true;
+}
+template <> bool compact_row_t<double>(const double* row, int64_t n, int32_t* idx, float* val, int64_t& k_out) {
+    int64_t k = 0, j = 0;
+    bool ok = true;
+    for (; j + 4 <= n; j += 4) {                                 // (three groups of four in four hold only zeros)
+        uint64_t u[4];
+        memcpy(u, row + j, 32);
+        if ((((u[0] | u[1]) | (u[2] | u[3])) << 1) == 0ull) continue;
+        for (int q = 0; q < 4; ++q) {
+            if ((u[q] << 1) == 0ull) continue;
+            float f;
+            ok &= to_f32_exact(row[j + q], f);
+            idx[k] = (int32_t)(j + q);
+            val[k] = f;
+            ++k;
+        }
+    }
+    for (; j < n; ++j) {
+        if (is_zero_bits(row + j)) continue;
+        float f;
+        ok &= to_f32_exact(row[j], f);
+        idx[k] = (int32_t)j;
+        val[k] = f;
+        ++k;
+    }
+    k_out = k;
+    return ok;
+}
+
+// Rows [c0, c0 + nc) of a strided host matrix (element (r, g) at base[r * rs + g * cs]; cs == 1: cell-major rows,
+// rs == 1: gene-major, the layout of a DataFrame block) -> CSR with float32 values, on `threads` host threads.
+// Returns false when a value is not exact in float32 or the rows turn out far denser than `density`.
+template <typename T>
+bool compact_block(const T* base, int64_t rs, int64_t cs, int64_t c0, int64_t nc, int64_t G, int threads, double density,
+                   std::vector<RawBuf<int32_t>>& t_idx, std::vector<RawBuf<float>>& t_val, std::vector<int64_t>& indptr,
+                   RawBuf<int32_t>& indices, RawBuf<float>& values) {
+    indptr.assign((size_t)nc + 1, 0);
+    std::vector<int> bad((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t r0 = nc * t / threads, r1 = nc * (t + 1) / threads;
+        RawBuf<int32_t>& ix = t_idx[(size_t)t];
+        RawBuf<float>& vv = t_val[(size_t)t];
+        size_t used = 0;
+        const size_t guess = (size_t)((double)(r1 - r0) * (double)G * std::min(1.0, density * 1.25 + 0.01)) + (size_t)G + 8;
+        ix.grow(guess, 0);
+        vv.grow(guess, 0);
+        bool ok = true;
+        if (cs == 1) {
+            for (int64_t r = r0; r < r1; ++r) {
+                if (ix.size() < used + (size_t)G + 8) {          // denser than the probe said: grow
+                    const size_t want = ix.size() + ix.size() / 2 + (size_t)G + 8;
+                    ix.grow(want, used);
+                    vv.grow(want, used);
+                }
+                int64_t k = 0;
+                ok &= compact_row_t<T>(base + (c0 + r) * rs, G, ix.data() + used, vv.data() + used, k);
+                indptr[(size_t)r + 1] = k;                       // (row length for now)
+                used += (size_t)k;
+            }
+        } else {
+            // gene-major: tiles of kTile cells; a gene contributes kTile consecutive values, whose non-zeros are appended
+            // to their cells' lists (fixed capacity per cell inside the tile: overflow = far denser than expected)
+            constexpr int kTile = 128;
+            int64_t capR = std::min<int64_t>(G, (int64_t)((double)G * density * 2.0) + 256);
+            RawBuf<int32_t> tix;
+            RawBuf<float> tvv;
+            tix.grow((size_t)(kTile * capR), 0);
+            tvv.grow((size_t)(kTile * capR), 0);
+            int64_t cur[kTile];
+            for (int64_t t0 = r0; t0 < r1 && ok; t0 += kTile) {
+                const int64_t tn = std::min<int64_t>(kTile, r1 - t0);
+                for (;;) {
+                    bool overflow = false;
+                    for (int64_t i = 0; i < tn; ++i) cur[i] = 0;
+                    for (int64_t g = 0; g < G; ++g) {
+                        const T* col = base + g * cs + (c0 + t0) * rs;      // (rs == 1: tn consecutive values)
+                        for (int64_t i = 0; i < tn; ++i) {
+                            if (is_zero_bits(col + i * rs)) continue;
+                            float f;
+                            ok &= to_f32_exact(col[i * rs], f);
+                            const int64_t k = cur[i];
+                            if (k >= capR) { overflow = true; continue; }
+                            tix.data()[i * capR + k] = (int32_t)g;
+                            tvv.data()[i * capR + k] = f;
+                            cur[i] = k + 1;
+                        }
+                    }
+                    if (!overflow) break;
+                    capR = std::min<int64_t>(G, capR * 2);       // a cell far denser than the sample: once more, with room
+                    tix.grow((size_t)(kTile * capR), 0);
+                    tvv.grow((size_t)(kTile * capR), 0);
+                }
+                size_t need = used;
+                for (int64_t i = 0; i < tn; ++i) need += (size_t)cur[i];
+                if (ix.size() < need + 8) {
+                    const size_t want = std::max(need + 8, ix.size() + ix.size() / 2);
+                    ix.grow(want, used);
+                    vv.grow(want, used);
+                }
+                for (int64_t i = 0; i < tn; ++i) {
+                    memcpy(ix.data() + used, tix.data() + i * capR, sizeof(int32_t) * (size_t)cur[i]);
+                    memcpy(vv.data() + used, tvv.data() + i * capR, sizeof(float) * (size_t)cur[i]);
+                    indptr[(size_t)(t0 + i) + 1] = cur[i];
+                    used += (size_t)cur[i];
+                }
+            }
+        }
+        bad[(size_t)t] = ok ? 0 : 1;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) {
+            try { pool.emplace_back(work, t); } catch (...) { work(t); }
+        }
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    for (int b : bad) if (b) return false;
+    for (int64_t r = 0; r < nc; ++r) indptr[(size_t)r + 1] += indptr[(size_t)r];
+    const int64_t nnz = indptr[(size_t)nc];
+    indices.grow((size_t)nnz + 8, 0);
+    values.grow((size_t)nnz + 8, 0);
+    auto gather = [&](int t) {
+        const int64_t r0 = nc * t / threads, r1 = nc * (t + 1) / threads;
+        const int64_t e0 = indptr[(size_t)r0], e1 = indptr[(size_t)r1];
+        memcpy(indices.data() + e0, t_idx[(size_t)t].data(), sizeof(int32_t) * (size_t)(e1 - e0));
+        memcpy(values.data() + e0, t_val[(size_t)t].data(), sizeof(float) * (size_t)(e1 - e0));
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) {
+            try { pool.emplace_back(gather, t); } catch (...) { gather(t); }
+        }
+        gather(0);
+        for (auto& th : pool) th.join();
+    }
+    return true;
+}
+}  // extern "C++"
+
+int host_threads();
+
+extern "C++" {
+// A sparse host matrix (dense storage, any of the two layouts, float32 or float64) through the CSR host call.
+// kNotCompacted: more than 30 % of a sample of its entries are non-zero, or a value does not survive the cast to float32
+// (nothing has been written to the outputs that the caller cannot overwrite).
+template <typename T>
+int dense_host_via_csr(const aucell_plan* p, const T* base, int64_t n_cells, int64_t rs, int64_t cs, double* h_out_auc,
+                       int32_t* h_out_nnz) {
+    const int64_t G = p->n_genes, R = p->n_regulons;
+    if (G < 64 || n_cells * G < ((int64_t)1 << 22)) return kNotCompacted;
+    // density of a sample: 64 evenly spaced cells x up to 4096 evenly spaced genes
+    const int64_t pc = std::min<int64_t>(n_cells, 64), pg = std::min<int64_t>(G, 4096);
+    int64_t nz = 0;
+    for (int64_t a = 0; a < pc; ++a)
+        for (int64_t b = 0; b < pg; ++b)
+            nz += is_zero_bits(base + (n_cells * a / pc) * rs + (G * b / pg) * cs) ? 0 : 1;
+    const double density = (double)nz / (double)(pc * pg);
+    if (density > 0.30) return kNotCompacted;
+    const int threads = host_threads();
+    // blocks of cells whose dense image is <= 1 GB: the CSR copy of a block stays small
+    const int64_t block = std::max<int64_t>(1024, ((int64_t)1 << 30) / (int64_t)sizeof(T) / std::max<int64_t>(G, 1));
+    std::vector<RawBuf<int32_t>> t_idx((size_t)threads);
+    std::vector<RawBuf<float>> t_val((size_t)threads);
+    std::vector<int64_t> indptr;
+    RawBuf<int32_t> indices;
+    RawBuf<float> values;
+    for (int64_t c0 = 0; c0 < n_cells; c0 += block) {
+        const int64_t nc = std::min(n_cells, c0 + block) - c0;
+        const auto tc0 = std::chrono::steady_clock::now();
+        if (!compact_block<T>(base, rs, cs, c0, nc, G, threads, density, t_idx, t_val, indptr, indices, values)) {
+            if (c0 == 0) return kNotCompacted;
+            return fail(AUCELL_ERR_INVALID, "expression values that are not exact in float32 appear late in the matrix: "
+                                            "pass float64 device chunks instead");
+        }
+        const auto tc1 = std::chrono::steady_clock::now();
+        const int rc = aucell_csr_f32_host(p, indptr.data(), indices.data(), values.data(), nc, h_out_auc + c0 * R,
+                                           h_out_nnz ? h_out_nnz + c0 : nullptr, 0);
+        if (getenv("AUCELL_B200_DEBUG"))
+            fprintf(stderr, "[aucell_b200] dense host call: %lld cells x %lld genes -> %lld stored entries (%.1f %%), "
+                            "squeezed in %.3f s, CSR call %.3f s\n",
+                    (long long)nc, (long long)G, (long long)indptr[(size_t)nc],
+                    100.0 * (double)indptr[(size_t)nc] / ((double)nc * (double)G),
+                    std::chrono::duration<double>(tc1 - tc0).count(),
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - tc1).count());
+        if (rc) return rc;
+    }
+    return AUCELL_OK;
+}
+}  // extern "C++"
+
 int host_threads() {
     const char* env = getenv("AUCELL_B200_HOST_THREADS");
     if (env && *env) return std::max(1, std::min(64, atoi(env)));
@@ -961,6 +1238,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     bool val8 = val8_allowed && (p->hint_val8 || val8_forced);
     std::unique_ptr<ValueDict> dict(val8 ? new (std::nothrow) ValueDict() : nullptr);
     if (val8 && !dict) val8 = false;
+    const auto t_call0 = std::chrono::steady_clock::now();
+    double t_alloc = 0.0, t_drain = 0.0;  // (debug) seconds spent growing the staging / copying AUC blocks out
     double narrow_ns = 0.0;               // time spent narrowing and entries narrowed so far in this call
     int64_t narrow_n = 0;
     int narrow_chunks = 0;
@@ -974,22 +1253,48 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     const bool out_pageable = is_pageable(h_out_auc) || (h_out_nnz && is_pageable(h_out_nnz));
     const int n_threads = (idx16 || val8 || in_pageable || out_pageable) ? host_threads() : 1;
     const size_t out_block = sizeof(double) * (size_t)chunk_cells * R;
+    const auto t_al0 = std::chrono::steady_clock::now();
     int rc = ensure_host_slots(host_slots, bytes,
                                in_pageable ? sizeof(int32_t) * (size_t)max_nnz : (idx16_allowed ? sizeof(uint16_t) * (size_t)max_nnz : 0),
                                in_pageable ? sizeof(float) * (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax
                                            : (val8 ? (size_t)max_nnz + sizeof(uint32_t) * ValueDict::kMax : 0),
                                out_pageable ? out_block + sizeof(int32_t) * (size_t)chunk_cells : 0);
     if (rc) return rc;
+    t_alloc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_al0).count();
     auto drain_out = [&](aucell_plan::HostSlot& s) -> cudaError_t {      // the slot's pending AUC block -> the caller's arrays
         if (s.out_nc == 0) return cudaSuccess;
         const cudaError_t e = cudaStreamSynchronize(s.st);
         if (e == cudaSuccess) {
+            const auto td0 = std::chrono::steady_clock::now();
             copy_bytes(h_out_auc + s.out_c0 * R, s.pin_out, sizeof(double) * (size_t)s.out_nc * R, n_threads);
             if (h_out_nnz) memcpy(h_out_nnz + s.out_c0, s.pin_out + out_block, sizeof(int32_t) * (size_t)s.out_nc);
+            t_drain += std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
         }
         s.out_nc = 0;
         return e;
     };
+    std::thread drainer;
+    cudaError_t drain_err = cudaSuccess;
+    // a fresh output array (np.zeros / np.empty) has no pages yet: let the kernel map them in bulk on helper threads
+    // instead of one fault per 4 KB inside the copy-out (Linux >= 5.14; elsewhere the call fails and nothing is lost)
+    std::vector<std::thread> prefault;
+    if (out_pageable && is_pageable(h_out_auc) && sizeof(double) * (size_t)n_cells * R >= ((size_t)32 << 20)) {
+        const uintptr_t b = ((uintptr_t)h_out_auc + 4095) & ~(uintptr_t)4095;
+        const uintptr_t e = ((uintptr_t)h_out_auc + sizeof(double) * (size_t)n_cells * R) & ~(uintptr_t)4095;
+        const int parts = 4;
+        for (int q = 0; q < parts && e > b; ++q) {
+            const uintptr_t qb = b + (((e - b) / parts * q) & ~(uintptr_t)4095);
+            const uintptr_t qe = q + 1 == parts ? e : b + (((e - b) / parts * (q + 1)) & ~(uintptr_t)4095);
+            try {
+                prefault.emplace_back([qb, qe]() {
+#ifdef __linux__
+                    if (qe > qb) madvise((void*)qb, qe - qb, 23 /* MADV_POPULATE_WRITE */);
+#endif
+                });
+            } catch (...) {
+            }
+        }
+    }
     int k = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, k = (k + 1) % kHostSlots) {
@@ -1005,7 +1310,22 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
         const int64_t nc = c1 - c0;
         const int64_t e0 = h_indptr[c0], ne = h_indptr[c1] - e0;
         bool chunk8 = false;
-        if (out_pageable) CKB(drain_out(s));
+        // the AUC block waiting in this slot goes out to the caller's (pageable) array on a helper thread, while this
+        // thread prepares and enqueues the next chunk; joined before the slot's landing zone is written again
+        if (out_pageable && s.out_nc != 0) {
+            if (drainer.joinable()) drainer.join();
+            if (drain_err != cudaSuccess) { rc = fail_cuda(drain_err, "cudaStreamSynchronize", __LINE__); break; }
+            aucell_plan::HostSlot* const ps = &s;
+            const int dev = p->device;
+            try {
+                drainer = std::thread([&drain_err, &drain_out, ps, dev]() {
+                    cudaSetDevice(dev);
+                    drain_err = drain_out(*ps);
+                });
+            } catch (...) {
+                CKB(drain_out(s));
+            }
+        }
         // stream order on the slot's stream protects its buffers from the previous chunk that used them
         CKB(cudaMemcpyAsync(d_indptr, h_indptr + c0, sizeof(int64_t) * (nc + 1), cudaMemcpyHostToDevice, s.st));
         h2d_bytes += (int64_t)sizeof(int64_t) * (nc + 1);
@@ -1101,6 +1421,8 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
             if (ns > (double)rate_n / 4.5) idx16 = false;        // < 4.5 G entries/s
         }
         if (out_pageable) {
+            if (drainer.joinable()) drainer.join();
+            if (drain_err != cudaSuccess) { rc = fail_cuda(drain_err, "cudaStreamSynchronize", __LINE__); break; }
             CKB(cudaMemcpyAsync(s.pin_out, d_auc, sizeof(double) * nc * R, cudaMemcpyDeviceToHost, s.st));
             if (h_out_nnz) CKB(cudaMemcpyAsync(s.pin_out + out_block, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
             s.out_c0 = c0;
@@ -1110,6 +1432,9 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
             if (h_out_nnz) CKB(cudaMemcpyAsync(h_out_nnz + c0, d_nnz, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s.st));
         }
     }
+    if (drainer.joinable()) drainer.join();
+    if (drain_err != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(drain_err, "cudaStreamSynchronize", __LINE__);
+    for (auto& th : prefault) th.join();
     for (auto& s : host_slots) {
         cudaError_t e = cudaStreamSynchronize(s.st);
         if (e != cudaSuccess && rc == AUCELL_OK) rc = fail_cuda(e, "cudaStreamSynchronize", __LINE__);
@@ -1124,9 +1449,11 @@ int aucell_csr_f32_host(const aucell_plan_t* p, const int64_t* h_indptr, const i
     }
     if (const char* dbg = getenv("AUCELL_B200_DEBUG"); dbg && dbg[0] == '1')
         fprintf(stderr, "[aucell_b200] csr host call: %lld cells, %lld entries, host prep %.3f s (%.2f G entries/s, %d threads), "
-                        "idx16 %d val8 %d, h2d %.2f GB d2h %.2f GB\n", (long long)n_cells, (long long)total_nnz, narrow_ns * 1e-9,
+                        "idx16 %d val8 %d, h2d %.2f GB d2h %.2f GB; %.3f s in all (staging %.3f s, copy-out %.3f s, pageable in %d out %d, "
+                        "chunks of %lld cells)\n", (long long)n_cells, (long long)total_nnz, narrow_ns * 1e-9,
                 narrow_ns > 0 ? (double)narrow_n / narrow_ns : 0.0, n_threads, (int)idx16, (int)val8, h2d_bytes * 1e-9,
-                d2h_bytes * 1e-9);
+                d2h_bytes * 1e-9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call0).count(), t_alloc,
+                t_drain, (int)in_pageable, (int)out_pageable, (long long)chunk_cells);
     return rc;
 }
 
@@ -1164,6 +1491,26 @@ int aucell_csr_is_canonical(const int64_t* h_indptr, const int32_t* h_indices, i
     return 1;
 }
 
+int aucell_dense_strided_host(const aucell_plan_t* p, const void* h_expr, int is_f64, int64_t n_cells,
+                              int64_t cell_stride, int64_t gene_stride, double* h_out_auc, int32_t* h_out_nnz) {
+    if (!p) return fail(AUCELL_ERR_INVALID, "plan is NULL");
+    if (p->n_regulons <= 0) return fail(AUCELL_ERR_INVALID, "plan has no regulons");
+    if (n_cells < 0) return fail(AUCELL_ERR_INVALID, "n_cells < 0");
+    if (n_cells == 0) return AUCELL_OK;
+    if (!h_expr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    const bool cell_major = gene_stride == 1 && cell_stride >= p->n_genes;
+    const bool gene_major = cell_stride == 1 && gene_stride >= n_cells;
+    if (!cell_major && !gene_major) return fail(AUCELL_ERR_INVALID, "one of the two strides must be 1 and the other span the matrix");
+    if (!p->fast_ok || !p->fast_enabled) return AUCELL_NOT_SPARSE;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    const int rc = is_f64 ? dense_host_via_csr<double>(p, static_cast<const double*>(h_expr), n_cells, cell_stride, gene_stride,
+                                                       h_out_auc, h_out_nnz)
+                          : dense_host_via_csr<float>(p, static_cast<const float*>(h_expr), n_cells, cell_stride, gene_stride,
+                                                      h_out_auc, h_out_nnz);
+    return rc == kNotCompacted ? AUCELL_NOT_SPARSE : rc;
+}
+
 int aucell_b200_release_staging(int device) {
     std::vector<DeviceStaging*> which;
     {
@@ -1191,11 +1538,19 @@ int aucell_dense_f32_host(const aucell_plan_t* p, const float* h_expr, int64_t n
     if (!h_expr || !h_out_auc) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     DeviceGuard dg(p->device);
     if (!dg.ok) return fail(AUCELL_ERR_CUDA, "cudaSetDevice failed");
+    const int64_t R = p->n_regulons;
+    // Sparse rows (what expression matrices are): squeeze the zeros out on the host and continue as a CSR call.
+    {
+        const char* envc = getenv("AUCELL_B200_HOST_COMPACT");
+        if (p->fast_ok && p->fast_enabled && chunk_cells <= 0 && !(envc && envc[0] == '0')) {
+            const int rc = dense_host_via_csr<float>(p, h_expr, n_cells, row_stride, 1, h_out_auc, h_out_nnz);
+            if (rc != kNotCompacted) return rc;
+        }
+    }
     DeviceStaging& staging = staging_of(p->device);
     std::lock_guard<std::mutex> staging_lock(staging.mu);
     std::lock_guard<std::mutex> host_lock(p->host_mu);
     std::vector<aucell_plan::HostSlot>& host_slots = staging.slots;
-    const int64_t R = p->n_regulons;
     if (chunk_cells <= 0)
         chunk_cells = std::max<int64_t>(256, (int64_t)(128.0 * 1024 * 1024 / (4.0 * (double)row_stride)));
     chunk_cells = std::min(chunk_cells, n_cells);

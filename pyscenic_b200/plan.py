@@ -267,6 +267,27 @@ class AUCellPlan:
         )
         return (out, nnz) if want_nnz else out
 
+    def aucell_dense_strided_host(self, values: np.ndarray, out: np.ndarray) -> bool:
+        """A dense host matrix as a DataFrame holds it (float32 / float64, cell-major or gene-major) through the library's
+        squeeze-the-zeros-out path (``aucell_dense_strided_host``).  False: not applicable (layout, density, values that
+        are not exact in float32) -- nothing computed, use another path."""
+        v = values
+        if v.ndim != 2 or v.dtype not in (np.float32, np.float64) or v.size == 0 or not out.flags.c_contiguous:
+            return False
+        es = v.dtype.itemsize
+        if v.strides[0] % es or v.strides[1] % es:
+            return False
+        s0, s1 = v.strides[0] // es, v.strides[1] // es
+        n_cells, n_genes = v.shape
+        if not ((s1 == 1 and s0 >= n_genes) or (s0 == 1 and s1 >= n_cells)):
+            return False
+        rc = self._lib.aucell_dense_strided_host(self._handle, v.ctypes.data, 1 if v.dtype == np.float64 else 0, n_cells,
+                                                 s0, s1, out.ctypes.data, None)
+        if rc == 1:
+            return False
+        _native.check(rc)
+        return True
+
     def aucell_csr_host(self, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, want_nnz: bool = False,
                         chunk_cells: int = 0, out: Optional[np.ndarray] = None):
         ip = np.ascontiguousarray(indptr, dtype=np.int64)

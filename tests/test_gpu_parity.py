@@ -929,3 +929,73 @@ def test_randomised_differential_fuzz_short():
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_gpu.py"), "12", "7"], cwd=root,
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_dense_host_call_squeezes_zeros_out_on_the_host(unweighted, monkeypatch):
+    """aucell_dense_f32_host on a sparse dense matrix: the host threads drop the zeros (AVX2 compress) and the call
+    continues as a CSR call.  Bit-identical to the dense device path and to the CSR entry point -- with -0.0, NaN, +inf,
+    negatives, an all-zero row and a row stride larger than the gene count in the matrix -- and switched off
+    (AUCELL_B200_HOST_COMPACT=0, or a dense matrix) the result is the same."""
+    import scipy.sparse as sp
+
+    n_cells, n_genes, stride = 800, 6011, 6016
+    rs = np.random.RandomState(5)
+    X = synth.dense_counts(rs, n_cells, n_genes, density=0.08)
+    X[3] = 0.0
+    X[5, rs.choice(n_genes, 40, replace=False)] = -1.5
+    X[6, 17] = np.nan
+    X[7, 23] = np.inf
+    X[8, rs.choice(n_genes, 100, replace=False)] = -0.0
+    X[9, -9:] = 3.0                                       # entries in the scalar remainder of the row
+    buf = np.full((n_cells, stride), 7.0, dtype=np.float32)          # (the padding must never be read as genes)
+    buf[:, :n_genes] = X
+    view = buf[:, :n_genes]
+    reg = synth.make_regulons(rs, n_genes, 80, 10, 300, weighted=not unweighted)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(3).permutation(n_genes)
+    m = sp.csr_matrix(X)
+    from pyscenic_b200 import _native
+
+    lib = _native.load()
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted=unweighted) as plan:
+        want = plan.aucell_dense(cuda(X)).cpu().numpy()
+        want_csr = plan.aucell_csr(cuda(m.indptr.astype(np.int64)), cuda(m.indices.astype(np.int32)), cuda(m.data)).cpu().numpy()
+        assert np.array_equal(want, want_csr)
+
+        def host_call(arr, row_stride):
+            out = np.full((n_cells, len(reg[0])), -1.0)
+            nnz = np.full(n_cells, -1, dtype=np.int32)
+            _native.check(lib.aucell_dense_f32_host(plan._handle, arr.ctypes.data, n_cells, row_stride, out.ctypes.data,
+                                                    nnz.ctypes.data, 0))
+            return out, nnz
+
+        got, nnz = host_call(buf, stride)                 # squeezed on the host (n_cells * n_genes >= 2^22, 8 % dense)
+        assert np.array_equal(got, want)
+        assert np.array_equal(nnz, np.count_nonzero(view, axis=1))
+        monkeypatch.setenv("AUCELL_B200_HOST_COMPACT", "0")
+        got0, nnz0 = host_call(buf, stride)               # uploaded as it is
+        assert np.array_equal(got0, want) and np.array_equal(nnz0, nnz)
+        monkeypatch.delenv("AUCELL_B200_HOST_COMPACT")
+        # the layouts and float types a DataFrame block comes in (aucell_dense_strided_host)
+        for dt in (np.float32, np.float64):
+            for order in ("C", "F"):
+                arr = np.asarray(X, dtype=dt, order=order)
+                out = np.full_like(want, -1.0)
+                assert plan.aucell_dense_strided_host(arr, out), (dt, order)
+                assert np.array_equal(out, want), (dt, order)
+        gm = np.asfortranarray(buf)[:, :n_genes]          # gene-major with a gene stride larger than the cell count
+        gm_rows = gm[100:]
+        out = np.full((n_cells - 100, want.shape[1]), -1.0)
+        assert plan.aucell_dense_strided_host(gm_rows, out) and np.array_equal(out, want[100:])
+        inexact = X.astype(np.float64)
+        inexact[11, 5] = 0.1                              # not a float32 value: the cast would change it
+        assert not plan.aucell_dense_strided_host(inexact, np.empty_like(want))
+        assert not plan.aucell_dense_strided_host(np.asfortranarray(inexact), np.empty_like(want))
+    Xd = np.where(rs.random_sample((n_cells, n_genes)) < 0.6, X.max() + rs.random_sample((n_cells, n_genes)), 0).astype(np.float32)
+    with _plan_for(n_genes, perm, reg, cutoff, unweighted=unweighted) as plan:       # 60 % dense: stays dense
+        want_d = plan.aucell_dense(cuda(Xd)).cpu().numpy()
+        out = np.full((n_cells, len(reg[0])), -1.0)
+        _native.check(lib.aucell_dense_f32_host(plan._handle, Xd.ctypes.data, n_cells, n_genes, out.ctypes.data, None, 0))
+        assert np.array_equal(out, want_d)
