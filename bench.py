@@ -3,7 +3,7 @@
 """
 bench.py -- AUCell cells/s on B200 (BASELINE.json metric), with roofline and CPU-reference figures.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|cfg2|rank]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -500,13 +500,93 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_rank_workload(args):
+    """--workload rank: create_rankings (reference aucell.py:25-51) alone, on a dense float32 matrix of the cfg4 gene
+    count as a DataFrame holds it -- the secondary kernel path (aucell_rank_dense_f32).  One GPU.  Reads 4 bytes and
+    writes 4 bytes (one uint32 rank) per gene and cell: the roofline counts both."""
+    import pandas as pd
+    import torch
+
+    import synth
+    from oracle import aucell_oracle as O
+    from pyscenic_b200 import _native
+    from pyscenic_b200.plan import AUCellPlan
+
+    n_cells, n_genes = args.cells or 40_000, 27_998
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    perm = np.random.RandomState(SEED).permutation(n_genes)
+    indptr, indices, data = synth.synth_csr_torch(n_cells, n_genes, 1960, seed=1000, device=dev)
+    X = torch.zeros((n_cells, n_genes), dtype=torch.float32, device=dev)
+    rows = torch.repeat_interleave(torch.arange(n_cells, device=dev), (indptr[1:] - indptr[:-1]))
+    X[rows, indices.long()] = data
+    del rows
+    ranks = torch.empty((n_cells, n_genes), dtype=torch.int32, device=dev)
+    alg_bytes = 8 * n_genes * n_cells
+    with AUCellPlan(n_genes, perm, None, device=0) as plan:
+        for _ in range(args.warmup):
+            plan.rank_dense(X, out=ranks)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(0)
+        sampler.start()
+        l0 = _native.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            plan.rank_dense(X, out=ranks)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        launches = _native.launch_count() - l0
+        clocks = sampler.stop()
+        csr_ranks = plan.rank_csr(indptr, indices, data)
+        same_as_csr = bool(torch.equal(csr_ranks, ranks))
+        del csr_ranks
+        # end to end: host float32 matrix -> host uint32 rankings through the product's create_rankings()
+        n_e = min(n_cells, 8192)
+        from pyscenic_b200.aucell import create_rankings
+
+        frame = pd.DataFrame(X[:n_e].cpu().numpy(), columns=["g%d" % j for j in range(n_genes)])
+        create_rankings(frame.iloc[:256], seed=SEED)
+        t0 = time.perf_counter()
+        got = create_rankings(frame, seed=SEED)
+        dt = time.perf_counter() - t0
+    n_s = min(args.ref_cells, n_e)
+    t0 = time.perf_counter()
+    want = O.create_rankings(frame.iloc[:n_s], seed=SEED)          # the reference's own pandas call chain
+    cpu_s = time.perf_counter() - t0
+    exact = bool(np.array_equal(got.iloc[:n_s].values, want.values) and list(got.columns) == list(want.columns))
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms / 1e3) / 1e9
+    print(json.dumps({
+        "metric": "create_rankings_cells_per_sec", "value": n_cells / (ms / 1e3), "unit": "cells/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 keys -> u32 ranks", "data": "synthetic",
+        "config": {"workload": "create_rankings on %d cells x %d genes dense f32 (~1,960 non-zero per cell), seed %d"
+                               % (n_cells, n_genes, SEED),
+                   "l2": "input + output (%.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": n_e / dt, "unit": "cells/s", "h2d_bytes_per_step": 4 * n_e * n_genes,
+                "d2h_bytes_per_step": 4 * n_e * n_genes, "cells": n_e,
+                "what": "pyscenic_b200.aucell.create_rankings(DataFrame float32) -> DataFrame uint32, pageable memory"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "aucell_fused_kernel<dense, RANKS>",
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "bytes_per_cell": 8 * n_genes},
+        "cpu_baseline": {"value": n_s / cpu_s, "unit": "cells/s", "cores": 1, "kind": "port",
+                         "sample": "first %d cells; the reference's pandas sample + rank(method='first') chain" % n_s},
+        "parity": {"cells": n_s, "bit_exact": exact, "dense_equals_csr_path": same_as_csr},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + ["rank"])
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (debugging)")
     ap.add_argument("--ref-cells", type=int, default=2048, help="cells in the CPU reference sample")
     ap.add_argument("--unweighted", action="store_true", help="unit gene weights (the CLI default of the reference)")
@@ -521,6 +601,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "rank":                # secondary workload (create_rankings alone): one GPU, our arm only
+        if rank == 0:
+            run_rank_workload(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
-tail -4 gpurun_out/pytest_gpu.log
-AUCELL_B200_DEBUG=1 timeout 600 python scripts/profile_api.py > gpurun_out/profile_api.jsonl 2> gpurun_out/profile_api.err; cut -c1-700 gpurun_out/profile_api.jsonl; grep "aucell_b200\] csr host call: 300000" gpurun_out/profile_api.err | cut -c1-420; tail -3 gpurun_out/profile_api.err | cut -c1-300
+for v in 1 0; do
+export AUCELL_B200_DENSE_CSR=$v
+echo "== DENSE_CSR=$v"
+timeout 600 python bench.py --workload rank --steps 5 --warmup 3 2>/dev/null | cut -c1-200
+timeout 600 python bench.py --workload cfg2 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | cut -c1-200
+timeout 600 python bench.py --workload cfg2 --cells 100000 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | cut -c1-200
+done
