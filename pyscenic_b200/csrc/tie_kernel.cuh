@@ -282,7 +282,12 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
     using VT = TieVal<IN>;
     using RowT = TieRow<UNIT>;
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, grp = tid / kTG, gtid = tid % kTG, lane = tid & 31, gw = gtid >> 5;
+    const int tid = threadIdx.x, grp = tid / kTG;
+    // the thread's index inside its cell group, made opaque: at 64 registers per thread the compiler would otherwise
+    // re-derive it (S2R + shifts) and everything that follows from it all over the cell loop (7 % of the instructions)
+    int gtid = tid % kTG;
+    asm volatile("" : "+r"(gtid));
+    const int lane = gtid & 31, gw = gtid >> 5;
 
     // inv_perm -> shared memory, once per CTA
     uint16_t* const ip = reinterpret_cast<uint16_t*>(smem);

@@ -15,7 +15,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["shard_bounds", "shard_bounds_by_nnz", "gather_blocks", "global_column_max", "aucell_sharded",
-           "aucell_csr_shard_from_host", "scatter_csr_shards"]
+           "aucell_csr_shard_from_host", "aucell_csr_shard_to_shared_host", "scatter_csr_shards"]
 
 
 def shard_bounds(n_cells: int, world_size: int) -> List[Tuple[int, int]]:
@@ -86,6 +86,95 @@ def aucell_sharded(compute_shard: Callable[[int, int], "object"], n_cells: int, 
     if normalize:
         block = block / global_column_max(block, group)
     return gather_blocks(block, bounds, n_regulons, group=group, dst=dst)
+
+
+def _all_on_one_host(group=None) -> bool:
+    import socket
+
+    import torch.distributed as dist
+
+    names = [None] * dist.get_world_size(group)
+    dist.all_gather_object(names, socket.gethostname(), group=group)
+    return len(set(names)) == 1
+
+
+_SHARED_RESULT = {}      # (n_cells, n_regulons, dst, group id) -> (memmap, registered) : the job's result buffer, kept
+
+
+def _shared_result(n_cells: int, n_regulons: int, rows: Tuple[int, int], group, dst: int):
+    """The ``[n_cells x n_regulons]`` float64 result of a one-box job in shared host memory: rank ``dst`` creates a file
+    under /dev/shm, every rank maps it and page-locks the rows it will write (``cudaHostRegister``), so that its
+    device-to-host copies land there at full PCIe rate.  Created on first use and kept for later calls of the same
+    shape (like a pinned-memory pool: mapping, zero-filling and page-locking 5 GB costs about a second); the file name
+    is unlinked as soon as every rank holds the mapping."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    key = (n_cells, n_regulons, dst, id(group))
+    hit = _SHARED_RESULT.get(key)
+    if hit is not None:
+        return hit[0]
+    if not _all_on_one_host(group):
+        raise RuntimeError("the shared-host-memory result needs every rank on one box; use aucell_csr_shard_from_host")
+    rank = dist.get_rank(group)
+    name = [None]
+    if rank == dst:
+        name[0] = "/dev/shm/aucell_b200_%d_%s.f64" % (os.getpid(), os.urandom(6).hex())
+        with open(name[0], "wb") as f:
+            f.truncate(max(1, n_cells * n_regulons * 8))
+    dist.broadcast_object_list(name, src=dst, group=group)
+    full = np.memmap(name[0], dtype=np.float64, mode="r+", shape=(n_cells, n_regulons))
+    registered = False
+    c0, c1 = rows
+    if (c1 > c0 or rank == dst) and torch.cuda.is_available():
+        # `dst` page-locks the whole matrix (a host range that is only partly registered cannot be the source of one
+        # cudaMemcpy: whoever consumes the result would trip over it), the other ranks the rows they write
+        base = full.ctypes.data
+        end = (base + n_cells * n_regulons * 8 + 4095) & ~4095
+        b = base if rank == dst else (base + c0 * n_regulons * 8) & ~4095
+        e = end if rank == dst else min(end, (base + c1 * n_regulons * 8 + 4095) & ~4095)
+        registered = int(torch.cuda.cudart().cudaHostRegister(b, e - b, 0)) == 0
+    dist.barrier(group=group)
+    if rank == dst:
+        os.unlink(name[0])
+    _SHARED_RESULT[key] = (full, registered)
+    return full
+
+
+def aucell_csr_shard_to_shared_host(plan, h_indptr, h_indices, h_data, bounds: Sequence[Tuple[int, int]], group=None,
+                                    dst: int = 0, timings: Optional[dict] = None):
+    """The cell-sharded job on ONE box without any device-side gather: the ``[cells x regulons]`` float64 result lives in
+    shared host memory (``_shared_result``), and every rank lets the library's pipelined host call
+    (``aucell_csr_f32_host``: upload, kernels and download of consecutive chunks overlap) write its own cell range
+    straight into it -- each over its own PCIe link.  What is left of the "gather" is a barrier.  Returns the full
+    matrix on ``dst`` (a numpy array over the mapping, valid until the next call of the same shape) and ``None``
+    elsewhere.  ``h_indptr`` / ``h_indices`` / ``h_data``: this rank's cell range as torch CPU tensors or numpy arrays
+    (pinned for full PCIe rate)."""
+    import time
+
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    n_cells = bounds[-1][1]
+    R = plan.n_regulons
+    c0, c1 = bounds[rank]
+    t0 = time.perf_counter()
+    full = _shared_result(n_cells, R, (c0, c1), group, dst)
+    t1 = time.perf_counter()
+    if c1 > c0:
+        as_np = lambda t: t.numpy() if hasattr(t, "numpy") else np.asarray(t)
+        ip = np.ascontiguousarray(as_np(h_indptr), dtype=np.int64)
+        assert len(ip) == c1 - c0 + 1
+        ip = ip - ip[0]                       # (the shard's own entries start at 0)
+        plan.aucell_csr_host(ip, as_np(h_indices), as_np(h_data), out=full[c0:c1])
+    t2 = time.perf_counter()
+    dist.barrier(group=group)
+    t3 = time.perf_counter()
+    if timings is not None:
+        timings.update(setup_s=t1 - t0, upload_kernel_download_s=t2 - t1, barrier_s=t3 - t2)
+    return full if rank == dst else None
 
 
 def aucell_csr_shard_from_host(plan, h_indptr, h_indices, h_data, bounds: Sequence[Tuple[int, int]], group=None,

@@ -22,7 +22,7 @@ def main():
 
     import synth
     from pyscenic_b200.plan import AUCellPlan, derive_rank_cutoff
-    from pyscenic_b200.sharding import aucell_csr_shard_from_host, scatter_csr_shards
+    from pyscenic_b200.sharding import aucell_csr_shard_from_host, aucell_csr_shard_to_shared_host, scatter_csr_shards
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=60000)
@@ -51,10 +51,15 @@ def main():
     del s_ip, s_ix, s_dv
     timings = {}
     full = aucell_csr_shard_from_host(plan, h_ip, h_ix, h_dv, bounds, timings=timings)
+    t_shm = {}
+    full_shm = aucell_csr_shard_to_shared_host(plan, h_ip, h_ix, h_dv, bounds, timings=t_shm)      # no device-side gather
     if rank == 0:
         want = plan.aucell_csr(indptr, indices, data)
         got = full.to(dev)
         same = bool(torch.equal(got, want))
+        same_shm = bool(torch.equal(torch.from_numpy(np.ascontiguousarray(full_shm)).to(dev), want))
+        timings["identical_shared_host_memory"] = same_shm
+        timings["shared_host_memory"] = t_shm
         info = {}
         if not same:
             bad = (got != want).any(dim=1).nonzero().flatten()

@@ -67,3 +67,4 @@ def test_one_process_per_gpu_sharded_driver_is_bit_identical():
     res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     assert '"identical": true' in res.stdout, res.stdout[-3000:]
+    assert '"identical_shared_host_memory": true' in res.stdout, res.stdout[-3000:]      # result assembled in /dev/shm
