@@ -190,17 +190,14 @@ struct TieLayout { int group_stride, groups, smem; };
 // shared-memory carve-up of aucell_tie_kernel; fills the offsets of `a`
 inline TieLayout tie_layout(const aucell_plan* p, TieArgs& a, int cap) {
     const int ip_bytes = align16(((p->n_genes + 7) / 8) * 16);
-    int off = 0;
+    // fixed-size arrays first, at the compile-time offsets the kernel uses (tie_kernel.cuh: kTieO*)
+    a.o_misc = kTieOMisc; a.o_rep = kTieORep; a.o_code = kTieOCode; a.o_cnt = kTieOCnt; a.o_fix = kTieOFix;
+    int off = kTieOA;
     a.o_A = off; off = align16(off + ((p->n_words + 3) / 4) * 16 + 128);    // + 32 spare words invalid lanes OR into
     a.o_wpre = off; off = align16(off + p->n_words * 2);
-    a.o_rep = off; off = align16(off + (kTieNB + 4) * 4);                   // + the spare bin
-    a.o_code = off; off = align16(off + kTieNB);
     a.o_bpp = off; off = align16(off + (cap + 1) * 2);                      // + the spare slot
     a.o_bpc = off; off = align16(off + cap + 1);
-    a.o_cnt = off; off = align16(off + kTieD * kTG * 4);
-    a.o_fix = off; off = align16(off + kTieFix * 8);
     a.o_acc = off; off = align16(off + a.acc_words * 4);
-    a.o_misc = off; off = align16(off + kTieMiscWords * 4);
     TieLayout L;
     L.group_stride = off;
     const int64_t room = p->smem_optin - ip_bytes;
@@ -297,6 +294,10 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
         x->out_auc = out_auc; x->out_nnz = out_nnz;
         x->todo = *todo; x->todo_n = *todo_n;
         x->stats = p->d_tie_stats;
+    }
+    {
+        const char* envp = getenv("AUCELL_B200_TIE_PREFETCH");
+        a.prefetch = (envp && envp[0] == '0') ? 0 : 1;
     }
     if (use1 && use2) {                            // rows beyond the first kernel's cap: a list for the second
         a.long_list = *todo + n_cells;

@@ -48,11 +48,23 @@ constexpr int kTieNB = 1 << kTieNBLog;  // value bins over the cell's own range
 constexpr int kTieD = 16;               // value classes per cell (class 0 = tail)
 constexpr int kTieFix = 128;            // tail entries per cell
 constexpr int kTieMaxGroups = 4;        // cell groups per CTA (1024 threads)
-constexpr int kTieP6 = 2;               // items per thread and pass of P6 (their table rows are loaded together)
+constexpr int kTieP6 = 2;               // items whose table rows are loaded together in P6
+constexpr int kTieP6R = 4;              // items per thread and pass of P6 (their ranks are computed together)
 constexpr int kTieMiscWords = 128;      // per group: reductions, scan words, flags, chain list lengths
 constexpr int kTieU = 4;                // entries per thread and pass of the streaming loops (loads issued together)
 constexpr int kTieMaxCap = 4096;        // stored entries per cell (20-bit reciprocal in P3; u16 prefixes)
 constexpr uint32_t kTiePadU = 0x7FFFu;  // unit weights: accumulator indices stay below this (bit 31 of a row flags a chain)
+
+// aucell_tie_kernel: the arrays of a cell group whose size does not depend on the plan sit at compile-time offsets from
+// the group's base (their addresses then cost nothing: immediate offsets instead of a constant load and an add)
+constexpr int kTieOMisc = 0;                                         // kTieMiscWords words
+constexpr int kTieORep = kTieOMisc + kTieMiscWords * 4;              // [kTieNB + 4] u32
+constexpr int kTieOCode = kTieORep + (kTieNB + 4) * 4;               // [kTieNB] u8
+constexpr int kTieOCnt = kTieOCode + kTieNB;                         // [kTieD][kTG] u32
+constexpr int kTieOFix = kTieOCnt + kTieD * kTG * 4;                 // [kTieFix] uint2
+constexpr int kTieOA = kTieOFix + kTieFix * 8;                       // bitmap; the plan-sized arrays follow
+static_assert(kTieORep % 16 == 0 && kTieOCode % 16 == 0 && kTieOCnt % 16 == 0 && kTieOFix % 16 == 0 && kTieOA % 16 == 0,
+              "16-byte aligned arrays");
 
 // to-do reasons (statistics only)
 enum { TIE_ST_FAST = 0, TIE_ST_LONG = 1, TIE_ST_BADVAL = 2, TIE_ST_DUP = 3, TIE_ST_MIXED = 4, TIE_ST_TAIL = 5,
@@ -89,6 +101,7 @@ struct TieArgs {
     int32_t* long_list;                 // aucell_tie_kernel: rows longer than its cap (up to long_cap entries) go here,
     int32_t* long_n;                    //   for aucell_tie2_kernel (nullptr: everything goes to `todo`)
     int long_cap;
+    int prefetch;                       // aucell_tie_kernel: prefetch the next cell's entries into L2 during the scatter
     const int32_t* in_list;             // aucell_tie2_kernel: the cells to rank (nullptr: all n_cells)
     const int32_t* in_n;
     unsigned long long* stats;          // [TIE_ST_N]
@@ -198,11 +211,14 @@ template <bool UNIT>
 __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_s, const TieRow<UNIT>& row, uint32_t m,
                                                  uint32_t maskL, uint32_t dummy, uint32_t& start, uint32_t& cnt) {
     if constexpr (UNIT) {
+        // (a row that continues in a chain keeps {start} in its last two slots: they add 0 to the first slot's
+        // accumulator instead -- no per-lane dummy address to keep in a register)
         const bool chain = (row.a.y >> 31) != 0u;
+        (void)dummy;
         tie_slot_u(acc_s, row.a.x & 0xFFFFu, m);
         tie_slot_u(acc_s, row.a.x >> 16, m);
-        tie_slot_u(acc_s, chain ? dummy : (row.a.y & 0xFFFFu), m);
-        tie_slot_u(acc_s, chain ? dummy : (row.a.y >> 16), m);
+        tie_slot_u(acc_s, chain ? (row.a.x & 0xFFFFu) : (row.a.y & 0xFFFFu), chain ? 0u : m);
+        tie_slot_u(acc_s, chain ? (row.a.x & 0xFFFFu) : (row.a.y >> 16), chain ? 0u : m);
         start = row.a.y & 0x7FFFFFFFu;
         cnt = 0u;                                          // (read from xu[start] by the consumer)
         return chain;
@@ -211,7 +227,9 @@ __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_
         tie_slot_w(acc_s, row.a.x, row.a.y, m, a.L, maskL);
         tie_slot_w(acc_s, row.a.z, row.a.w, m, a.L, maskL);
         tie_slot_w(acc_s, row.b.x, row.b.y, m, a.L, maskL);
-        tie_slot_w(acc_s, chain ? 0u : row.b.z, chain ? dummy : row.b.w, m, a.L, maskL);
+        // (a chained row keeps {start, count} in its last slot: it adds 0 to the third slot's accumulator instead)
+        (void)dummy;
+        tie_slot_w(acc_s, chain ? 0u : row.b.z, chain ? row.b.y : row.b.w, m, a.L, maskL);
         start = row.b.z;
         cnt = row.b.w & 0x7FFFFFFFu;
         return chain;
@@ -297,17 +315,17 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         for (int i = tid; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(ip)[i] = __ldg(src + i);
     }
     unsigned char* const gb = smem + a.off_group0 + grp * a.group_stride;
-    uint32_t* const A = reinterpret_cast<uint32_t*>(gb + a.o_A);          // [n_words + pad] occupied positions
+    uint32_t* const A = reinterpret_cast<uint32_t*>(gb + kTieOA);          // [n_words + pad] occupied positions
     uint16_t* const wpre = reinterpret_cast<uint16_t*>(gb + a.o_wpre);    // [n_words] set bits before the word
-    uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + a.o_rep);      // [kTieNB + 4] value bits of the bin, 0 = empty;
+    uint32_t* const rep = reinterpret_cast<uint32_t*>(gb + kTieORep);      // [kTieNB + 4] value bits of the bin, 0 = empty;
                                                                           // from P6 on: the warps' chain lists
-    uint8_t* const code_of = reinterpret_cast<uint8_t*>(gb + a.o_code);   // [kTieNB] class of the bin
+    uint8_t* const code_of = reinterpret_cast<uint8_t*>(gb + kTieOCode);   // [kTieNB] class of the bin
     uint16_t* const bpp = reinterpret_cast<uint16_t*>(gb + a.o_bpp);      // [cap + 1] position of the j-th entry (chunk-interleaved)
     uint8_t* const bpc = reinterpret_cast<uint8_t*>(gb + a.o_bpc);        // [cap + 1] its class
-    uint32_t* const cnt = reinterpret_cast<uint32_t*>(gb + a.o_cnt);      // [kTieD][kTG] counters, then bases
-    uint2* const fix = reinterpret_cast<uint2*>(gb + a.o_fix);            // [kTieFix] (value bits, pos) of the tail
+    uint32_t* const cnt = reinterpret_cast<uint32_t*>(gb + kTieOCnt);      // [kTieD][kTG] counters, then bases
+    uint2* const fix = reinterpret_cast<uint2*>(gb + kTieOFix);            // [kTieFix] (value bits, pos) of the tail
     uint32_t* const acc = reinterpret_cast<uint32_t*>(gb + a.o_acc);      // accumulators, then 32 dummies
-    uint32_t* const misc = reinterpret_cast<uint32_t*>(gb + a.o_misc);    // kTieMiscWords words, see kM* below
+    uint32_t* const misc = reinterpret_cast<uint32_t*>(gb + kTieOMisc);    // kTieMiscWords words, see kM* below
     constexpr int kMScanA = 0;                 // [kTGW] scan words of P2
     constexpr int kMScanB = kTGW;              // [kTGW] scan words of P5
     constexpr int kMTail = 2 * kTGW;           // tail count
@@ -563,6 +581,21 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         }
         group_bar(barid);
 
+        // the next cell's stored entries on their way from DRAM to L2 while this cell scatters: its first pass (P1) then
+        // waits for L2, not for DRAM (one 128-byte line per thread and array)
+        if (a.prefetch) {
+            const int64_t nxt = cell + (int64_t)gridDim.x * a.groups;
+            if (nxt < a.n_cells) {
+                const int64_t nb = __ldg(a.indptr + nxt);
+                const int nn = (int)min((int64_t)cap, __ldg(a.indptr + nxt + 1) - nb);
+                const char* const pc = reinterpret_cast<const char*>(reinterpret_cast<const IdxT*>(a.indices) + nb);
+                const char* const pv = reinterpret_cast<const char*>(reinterpret_cast<const typename VT::type*>(a.data) + nb);
+                for (int o = gtid * 128; o < nn * (int)sizeof(IdxT); o += kTG * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+                for (int o = gtid * 128; o < nn * (int)sizeof(typename VT::type); o += kTG * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + o));
+            }
+        }
         // ---------------- P6: rank in position order with private counters, scatter -------------------------------
         // kTieP6 items per pass, the same number of passes for every thread of the group (threads past their chunk's
         // end work on the spare slot with multiplier 0): ranks first -- the counters are private, so this is a short
@@ -570,23 +603,45 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         // in a chain are put on the warp's list and applied afterwards.
         {
             const int j0 = gtid * ch, j1 = min(j0 + ch, npos);
-            const int passes = (ch + kTieP6 - 1) / kTieP6;
+            const int passes = (ch + kTieP6R - 1) / kTieP6R;
 #pragma unroll 1
             for (int it = 0; it < passes; ++it) {
-                const int j = j0 + it * kTieP6;
+                const int j = j0 + it * kTieP6R;
+                // ranks of kTieP6R items at once: their (position, class) and their class counters are loaded together
+                // -- the counter of a class that appears twice in the batch is bumped in registers, so no load waits
+                // for an earlier store that might alias it
+                uint32_t mm[kTieP6R];
+                unsigned ps[kTieP6R], cs[kTieP6R];
+                int rr[kTieP6R];
+#pragma unroll
+                for (int k = 0; k < kTieP6R; ++k) {
+                    const bool in = j + k < j1;
+                    const int jj = in ? (it * kTieP6R + k) * kTG + gtid : cap;
+                    ps[k] = bpp[jj];
+                    cs[k] = in ? (unsigned)bpc[jj] : 0u;       // (the tail class: its counters are never read)
+                }
+#pragma unroll
+                for (int k = 0; k < kTieP6R; ++k) rr[k] = (int)cnt[cs[k] * kTG + gtid];
+#pragma unroll
+                for (int k = 1; k < kTieP6R; ++k) {
+                    int before = 0;
+#pragma unroll
+                    for (int q = 0; q < k; ++q) before += (cs[q] == cs[k]) ? 1 : 0;
+                    rr[k] += before;
+                }
+#pragma unroll
+                for (int k = 0; k < kTieP6R; ++k) {
+                    cnt[cs[k] * kTG + gtid] = (uint32_t)(rr[k] + 1);      // (in order: the last of a class wins)
+                    mm[k] = (cs[k] != 0u && rr[k] < cutoff) ? (uint32_t)(cutoff - rr[k]) : 0u;
+                }
+#pragma unroll
+                for (int h = 0; h < kTieP6R; h += kTieP6) {
                 uint32_t m[kTieP6];
                 RowT row[kTieP6];
 #pragma unroll
                 for (int k = 0; k < kTieP6; ++k) {
-                    const bool in = j + k < j1;
-                    const int jj = in ? (it * kTieP6 + k) * kTG + gtid : cap;
-                    const unsigned pos = bpp[jj];
-                    const unsigned cc = bpc[jj];
-                    uint32_t* const ctr = cnt + cc * kTG + gtid;
-                    const int r = (int)*ctr;
-                    *ctr = (uint32_t)(r + 1);
-                    m[k] = (in && cc != 0u && r < cutoff) ? (uint32_t)(cutoff - r) : 0u;
-                    if (m[k]) row[k] = tie_load_row<UNIT>(a, pos);
+                    m[k] = mm[h + k];
+                    if (m[k]) row[k] = tie_load_row<UNIT>(a, ps[h + k]);
                 }
 #pragma unroll
                 for (int k = 0; k < kTieP6; ++k) {
@@ -609,6 +664,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                             }
                         }
                     }
+                }
                 }
             }
             // the warp's deferred chains, one per lane

@@ -1,9 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 1 0; do
-export AUCELL_B200_DENSE_CSR=$v
-echo "== DENSE_CSR=$v"
-timeout 600 python bench.py --workload rank --steps 5 --warmup 3 2>/dev/null | cut -c1-200
-timeout 600 python bench.py --workload cfg2 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | cut -c1-200
-timeout 600 python bench.py --workload cfg2 --cells 100000 --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | cut -c1-200
-done
+timeout 300 python scripts/dev_tie.py 200000 2>&1 | grep -E '"fast": 1|kernel 1' | cut -c1-130
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tie_class or byte_coded or config4 or config5" 2>&1 | tail -3

@@ -32,6 +32,44 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.aucell_b200_launch_count() >= 0
 
 
+def test_csr_is_canonical_host_check():
+    """aucell_csr_is_canonical (host threads, no GPU): what scipy's has_canonical_format says, plus the column range."""
+    import scipy.sparse as sp
+
+    lib = _native.load()
+
+    def check(indptr, indices, n_genes):
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        return lib.aucell_csr_is_canonical(ip.ctypes.data, ix.ctypes.data if len(ix) else None, len(ip) - 1, n_genes)
+
+    rs = np.random.RandomState(0)
+    m = sp.random(300, 500, density=0.05, format="csr", random_state=rs, dtype=np.float32)
+    m.sort_indices()
+    assert m.has_canonical_format and check(m.indptr, m.indices, 500) == 1
+    assert check(m.indptr, m.indices, int(m.indices.max())) == 0                  # a column out of range
+    bad = m.indices.copy()
+    r = int(np.argmax(np.diff(m.indptr) >= 2))
+    s0 = m.indptr[r]
+    bad[s0], bad[s0 + 1] = bad[s0 + 1], bad[s0]                                  # one row unsorted
+    assert check(m.indptr, bad, 500) == 0
+    dup = m.indices.copy()
+    dup[s0 + 1] = dup[s0]                                                        # a duplicate column
+    assert check(m.indptr, dup, 500) == 0
+    neg = m.indices.copy()
+    neg[s0] = -1
+    assert check(m.indptr, neg, 500) == 0
+    assert check([0, 0, 0], [], 10) == 1                                         # empty rows
+    assert check([0], [], 10) == 1                                               # no rows
+    assert lib.aucell_csr_is_canonical(None, None, 3, 10) < 0                    # bad arguments
+    big = sp.random(20000, 2000, density=0.02, format="csr", random_state=rs, dtype=np.float32)   # several threads
+    big.sort_indices()
+    assert check(big.indptr, big.indices, 2000) == 1
+    ix = big.indices.copy()
+    ix[-1] = 2000
+    assert check(big.indptr, ix, 2000) == 0
+
+
 def test_library_has_sm100a_code_only():
     import subprocess, shutil
 
