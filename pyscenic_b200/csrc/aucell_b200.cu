@@ -321,6 +321,13 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
             PCK(cudaMalloc(&p->d_tie_stats, TIE_ST_N * sizeof(unsigned long long)));
             PCK(cudaMemset(p->d_tie_stats, 0, TIE_ST_N * sizeof(unsigned long long)));
             if (p->weighted) {
+                {
+                    // few regulons per gene (measured: up to ~1.5 on average): three direct slots, six instead of
+                    // eight atomics per ranked gene, +4 % at 50..250 regulons; more: four slots, fewer chains
+                    const char* envs = getenv("AUCELL_B200_TIE_SLOTS");
+                    p->tie_slots = (envs && (envs[0] == '3' || envs[0] == '4')) ? envs[0] - '0'
+                                                                                : ((double)nT <= 1.5 * (double)n_genes ? 3 : 4);
+                }
                 std::vector<uint4> ell(2 * (size_t)n_genes);
                 std::vector<uint2> xw;
                 for (int64_t g = 0; g < n_genes; ++g) {
@@ -328,11 +335,13 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
                     // empty slots: W = 0 into one of the 32 dummy accumulator pairs behind the real ones
                     const uint32_t pad = (uint32_t)(2 * p->n_acc + 2 * (g & 31)) * 4u;
                     uint32_t sw[4] = {0u, 0u, 0u, 0u}, so[4] = {pad, pad, pad, pad};
-                    const uint32_t direct = len > 4 ? 3u : len;
+                    // (tie_slots == 3: the fourth slot only ever holds the chain, the kernel skips its atomics)
+                    const uint32_t nslots = (uint32_t)p->tie_slots;
+                    const uint32_t direct = len > nslots ? 3u : len;
                     // byte offset of an accumulator's low limb: the limbs swap places every 16 accumulators (tie_slot_w)
                     auto lo_off = [](uint32_t acc) { return acc * 8u + ((acc & 16u) ? 4u : 0u); };
                     for (uint32_t k = 0; k < direct; ++k) { sw[k] = (uint32_t)tw[b + k]; so[k] = lo_off(tacc[b + k]); }
-                    if (len > 4) {
+                    if (len > nslots) {
                         sw[3] = (uint32_t)xw.size();
                         so[3] = 0x80000000u | (len - 3);
                         for (uint32_t k = b + 3; k < e; ++k) xw.push_back(make_uint2((uint32_t)tw[k], lo_off(tacc[k])));

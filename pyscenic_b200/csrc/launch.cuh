@@ -99,6 +99,7 @@ struct aucell_plan {
     bool fast_ok = false;
     bool fast_enabled = true;                // aucell_plan_set_fast_path
     int tie_L = 0;                           // weighted: products are split at this bit
+    int tie_slots = 4;                       // weighted: direct slots per table row (3: the fourth only holds the chain)
     uint4* d_ell_w = nullptr;
     uint2* d_xw = nullptr;
     uint2* d_ell_u = nullptr;
@@ -286,6 +287,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
         x->inv_perm = p->d_inv_perm16;
         x->ell_w = p->d_ell_w; x->xw = p->d_xw; x->ell_u = p->d_ell_u; x->xu = p->d_xu;
         x->L = p->tie_L;
+        x->slots4 = p->tie_slots == 4 ? 1 : 0;
         x->n_regulons = p->n_regulons;
         x->acc_first = p->d_acc_first; x->acc_parts = p->d_acc_parts; x->acc_scale = p->d_acc_scale;
         x->reg_rec = p->d_reg_rec;

@@ -9,8 +9,12 @@
 //            ctxcore.recovery.enrichment4cells -> aucs -> auc2d -> weighted_auc1d     (third-party)
 //
 // Layout: ONE persistent CTA per SM; it keeps inv_perm (gene column -> shuffled position, uint16) resident in shared
-// memory and runs `groups` independent 128-thread cell groups, each with its own working set and its own named
-// barrier (bar.sync id, 128), so no phase ever waits for more than four warps.
+// memory and runs `groups` (four) independent 256-thread cell groups, each with its own working set and its own named
+// barrier (bar.sync id, 256), so no phase ever waits for more than eight warps.
+//
+// Two kernels live here: aucell_tie_kernel (position-ordered list + counting sort by class; rows up to 4,096 entries)
+// and, further down, aucell_tie2_kernel (one position bitmap per value class; rows up to 16,384 entries), which runs
+// behind the first on the rows beyond its capacity.  launch.cuh: launch_tie.
 //
 // rank(g) = #{genes with a larger value} + #{genes with the same value at a smaller shuffled position}.  Per cell:
 //   P0  value range     of a sample of the whole matrix (tie_range_kernel, one small CTA before this kernel).  Cells with
@@ -27,8 +31,8 @@
 //   P5  scan            exclusive scan of cnt in (class, chunk) order = rank of the first item of every chunk.
 //   P6  rank + scatter  thread t walks chunk t of by_pos in position order with PRIVATE counters
 //                       (rank = base[class][t]++: a stable counting sort by class, no atomics, no votes) and adds
-//                       W * (cutoff - rank) for every regulon holding the gene: the regulon table is ELL (two slots
-//                       per gene in one 128-bit load, chained overflow), accumulators are pairs of u32 limbs updated
+//                       W * (cutoff - rank) for every regulon holding the gene: the regulon table is ELL (four slots
+//                       per gene in two 128-bit loads, chained overflow), accumulators are pairs of u32 limbs updated
 //                       with non-returning shared atomics (the product is split at bit L, so no carry is needed).
 //   P7  tail            all pairs over the (<= 128) tail entries: rank = #{(value, pos) before mine}.
 //   P8  zeros           fewer positives than the cutoff: zeros fill the remaining ranks in position order.
@@ -85,6 +89,7 @@ struct TieArgs {
     const uint2* ell_u;                 // unit weights: [n_genes] four uint16 accumulators, or two + chain
     const uint16_t* xu;                 //           chained: count, accumulators...
     int L;                              // weighted: products are split at bit L
+    int slots4;                         // weighted: the fourth slot of a row may hold a regulon (else only a chain)
     int n_regulons;
     int acc_words;                      // u32 words of accumulators per group
     const int32_t* acc_first;           // [R] first accumulator of regulon r, -1 = invalid regulon
@@ -229,7 +234,7 @@ __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_
         tie_slot_w(acc_s, row.b.x, row.b.y, m, a.L, maskL);
         // (a chained row keeps {start, count} in its last slot: it adds 0 to the third slot's accumulator instead)
         (void)dummy;
-        tie_slot_w(acc_s, chain ? 0u : row.b.z, chain ? row.b.y : row.b.w, m, a.L, maskL);
+        if (a.slots4) tie_slot_w(acc_s, chain ? 0u : row.b.z, chain ? row.b.y : row.b.w, m, a.L, maskL);
         start = row.b.z;
         cnt = row.b.w & 0x7FFFFFFFu;
         return chain;

@@ -122,9 +122,19 @@ def _shared_result(n_cells: int, n_regulons: int, rows: Tuple[int, int], group, 
     name = [None]
     if rank == dst:
         name[0] = "/dev/shm/aucell_b200_%d_%s.f64" % (os.getpid(), os.urandom(6).hex())
-        with open(name[0], "wb") as f:
-            f.truncate(max(1, n_cells * n_regulons * 8))
+        try:
+            with open(name[0], "wb") as f:
+                # reserve the pages now: a /dev/shm that is too small must fail here, not with SIGBUS in the middle of a copy
+                os.posix_fallocate(f.fileno(), 0, max(1, n_cells * n_regulons * 8))
+        except OSError as e:
+            try:
+                os.unlink(name[0])
+            except OSError:
+                pass
+            name[0] = "!%s" % e
     dist.broadcast_object_list(name, src=dst, group=group)
+    if name[0].startswith("!"):
+        raise RuntimeError("no room for the result in /dev/shm (%s); use aucell_csr_shard_from_host" % name[0][1:])
     full = np.memmap(name[0], dtype=np.float64, mode="r+", shape=(n_cells, n_regulons))
     registered = False
     c0, c1 = rows
