@@ -322,11 +322,11 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
             PCK(cudaMemset(p->d_tie_stats, 0, TIE_ST_N * sizeof(unsigned long long)));
             if (p->weighted) {
                 {
-                    // few regulons per gene (measured: up to ~1.5 on average): three direct slots, six instead of
-                    // eight atomics per ranked gene, +4 % at 50..250 regulons; more: four slots, fewer chains
+                    // (32-byte rows -- plans with more than 991 accumulators; smaller plans use the compact rows below --:
+                    // four direct slots; AUCELL_B200_TIE_SLOTS=3 leaves the fourth to the chain, measured +4 % at 50..250
+                    // regulons and -1 % at 500)
                     const char* envs = getenv("AUCELL_B200_TIE_SLOTS");
-                    p->tie_slots = (envs && (envs[0] == '3' || envs[0] == '4')) ? envs[0] - '0'
-                                                                                : ((double)nT <= 1.5 * (double)n_genes ? 3 : 4);
+                    p->tie_slots = (envs && envs[0] == '3') ? 3 : 4;
                 }
                 std::vector<uint4> ell(2 * (size_t)n_genes);
                 std::vector<uint2> xw;
@@ -348,6 +348,37 @@ int aucell_plan_create(int device, int64_t n_genes, const int32_t* h_perm, int32
                     }
                     ell[2 * (size_t)g] = make_uint4(sw[0], so[0], sw[1], so[1]);
                     ell[2 * (size_t)g + 1] = make_uint4(sw[2], so[2], sw[3], so[3]);
+                }
+                // compact rows (one 128-bit load per ranked gene instead of two: the row gathers are a quarter of the
+                // kernel's L1 data-pipe traffic): three weights + three 10-bit accumulator indices, chains looked up by
+                // position.  When the accumulators (and the 32 dummies behind them) can be named in 10 bits.
+                {
+                    const char* env16 = getenv("AUCELL_B200_TIE_ROW16");
+                    if (p->n_acc + 32 <= 1023 && !(env16 && env16[0] == '0')) {
+                        std::vector<uint4> e16((size_t)n_genes);
+                        std::vector<uint2> xinfo((size_t)n_genes, make_uint2(0u, 0u));
+                        std::vector<uint2> xw16;
+                        auto lo_off16 = [](uint32_t acc) { return acc * 8u + ((acc & 16u) ? 4u : 0u); };
+                        for (int64_t g = 0; g < n_genes; ++g) {
+                            const uint32_t b = tptr[g], e = tptr[g + 1], len = e - b;
+                            const uint32_t padi = (uint32_t)p->n_acc + (uint32_t)(g & 31);
+                            uint32_t w3[3] = {0u, 0u, 0u}, i3[3] = {padi, padi, padi};
+                            const uint32_t direct = std::min<uint32_t>(len, 3u);
+                            for (uint32_t k = 0; k < direct; ++k) { w3[k] = (uint32_t)tw[b + k]; i3[k] = tacc[b + k]; }
+                            uint32_t pk = i3[0] | (i3[1] << 10) | (i3[2] << 20);
+                            if (len > 3) {
+                                pk |= 0x80000000u;
+                                xinfo[(size_t)g] = make_uint2((uint32_t)xw16.size(), len - 3);
+                                for (uint32_t k = b + 3; k < e; ++k) xw16.push_back(make_uint2((uint32_t)tw[k], lo_off16(tacc[k])));
+                            }
+                            e16[(size_t)g] = make_uint4(w3[0], w3[1], w3[2], pk);
+                        }
+                        xw.swap(xw16);             // the chained slots of THIS format (the 32-byte rows stay as a fallback table)
+                        PCK(cudaMalloc(&p->d_ell_w16, sizeof(uint4) * e16.size()));
+                        PCK(cudaMemcpy(p->d_ell_w16, e16.data(), sizeof(uint4) * e16.size(), cudaMemcpyHostToDevice));
+                        PCK(cudaMalloc(&p->d_xinfo, sizeof(uint2) * xinfo.size()));
+                        PCK(cudaMemcpy(p->d_xinfo, xinfo.data(), sizeof(uint2) * xinfo.size(), cudaMemcpyHostToDevice));
+                    }
                 }
                 if (xw.empty()) xw.push_back(make_uint2(0u, 0u));
                 PCK(cudaMalloc(&p->d_ell_w, sizeof(uint4) * ell.size()));
@@ -425,6 +456,8 @@ int aucell_plan_destroy(aucell_plan_t* p) {
     cudaFree(p->d_tent);
     cudaFree(p->d_tacc16);
     cudaFree(p->d_ell_w);
+    cudaFree(p->d_ell_w16);
+    cudaFree(p->d_xinfo);
     cudaFree(p->d_xw);
     cudaFree(p->d_ell_u);
     cudaFree(p->d_xu);

@@ -101,6 +101,8 @@ struct aucell_plan {
     int tie_L = 0;                           // weighted: products are split at this bit
     int tie_slots = 4;                       // weighted: direct slots per table row (3: the fourth only holds the chain)
     uint4* d_ell_w = nullptr;
+    uint4* d_ell_w16 = nullptr;              // weighted, compact rows (accumulator indices < 1024): see TieArgs::ell_w16
+    uint2* d_xinfo = nullptr;
     uint2* d_xw = nullptr;
     uint2* d_ell_u = nullptr;
     uint16_t* d_xu = nullptr;
@@ -286,6 +288,7 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
         x->cutoff = (int)p->rank_cutoff;
         x->inv_perm = p->d_inv_perm16;
         x->ell_w = p->d_ell_w; x->xw = p->d_xw; x->ell_u = p->d_ell_u; x->xu = p->d_xu;
+        x->ell_w16 = p->d_ell_w16; x->xinfo = p->d_xinfo; x->row16 = p->d_ell_w16 != nullptr ? 1 : 0;
         x->L = p->tie_L;
         x->slots4 = p->tie_slots == 4 ? 1 : 0;
         x->n_regulons = p->n_regulons;
@@ -300,6 +303,8 @@ int launch_tie(const aucell_plan* p, const int64_t* indptr, const void* indices,
     {
         const char* envp = getenv("AUCELL_B200_TIE_PREFETCH");
         a.prefetch = (envp && envp[0] == '0') ? 0 : 1;
+        const char* envk = getenv("AUCELL_B200_TIE_SKIP");
+        a.skip = envk ? atoi(envk) : 0;
     }
     if (use1 && use2) {                            // rows beyond the first kernel's cap: a list for the second
         a.long_list = *todo + n_cells;

@@ -56,6 +56,7 @@ constexpr int kTieP6 = 2;               // items whose table rows are loaded tog
 constexpr int kTieP6R = 4;              // items per thread and pass of P6 (their ranks are computed together)
 constexpr int kTieMiscWords = 128;      // per group: reductions, scan words, flags, chain list lengths
 constexpr int kTieU = 4;                // entries per thread and pass of the streaming loops (loads issued together)
+constexpr int kTieU1 = 8;               // the same in P1 of aucell_tie_kernel
 constexpr int kTieMaxCap = 4096;        // stored entries per cell (20-bit reciprocal in P3; u16 prefixes)
 constexpr uint32_t kTiePadU = 0x7FFFu;  // unit weights: accumulator indices stay below this (bit 31 of a row flags a chain)
 
@@ -86,6 +87,11 @@ struct TieArgs {
     const uint4* ell_w;                 // weighted: [2 * n_genes] four slots {W, off} per gene; a gene in more than
                                         //           four regulons keeps three and {start, count | 1 << 31} of a chain
     const uint2* xw;                    //           chained slots {W, off}
+    const uint4* ell_w16;               // weighted, compact rows (row16 != 0): [n_genes] {W0, W1, W2, idx0 | idx1 << 10 |
+                                        //           idx2 << 20 | chain << 31} -- accumulator INDICES (< 1024), one 128-bit
+                                        //           load per gene instead of two
+    const uint2* xinfo;                 //           [n_genes] {start, count} of the chain of a gene whose row has the flag
+    int row16;
     const uint2* ell_u;                 // unit weights: [n_genes] four uint16 accumulators, or two + chain
     const uint16_t* xu;                 //           chained: count, accumulators...
     int L;                              // weighted: products are split at bit L
@@ -107,6 +113,7 @@ struct TieArgs {
     int32_t* long_n;                    //   for aucell_tie2_kernel (nullptr: everything goes to `todo`)
     int long_cap;
     int prefetch;                       // aucell_tie_kernel: prefetch the next cell's entries into L2 during the scatter
+    int skip;                           // timing experiments only (AUCELL_B200_TIE_SKIP): 1 no scatter, 2 no epilogue, stop after 4: P2, 8: P3, 16: P5
     const int32_t* in_list;             // aucell_tie2_kernel: the cells to rank (nullptr: all n_cells)
     const int32_t* in_n;
     unsigned long long* stats;          // [TIE_ST_N]
@@ -171,6 +178,9 @@ __device__ __forceinline__ TieRow<UNIT> tie_load_row(const TieArgs& a, unsigned 
     TieRow<UNIT> r;
     if constexpr (UNIT) {
         r.a = __ldg(a.ell_u + pos);
+    } else if (a.row16) {
+        r.a = __ldg(a.ell_w16 + pos);
+        r.b = make_uint4(pos, 0u, 0u, 0u);                 // (the chain, if any, is looked up by position)
     } else {
         r.a = __ldg(a.ell_w + 2 * pos);
         r.b = __ldg(a.ell_w + 2 * pos + 1);
@@ -226,6 +236,24 @@ __device__ __forceinline__ bool tie_apply_direct(const TieArgs& a, uint32_t acc_
         tie_slot_u(acc_s, chain ? (row.a.x & 0xFFFFu) : (row.a.y >> 16), chain ? 0u : m);
         start = row.a.y & 0x7FFFFFFFu;
         cnt = 0u;                                          // (read from xu[start] by the consumer)
+        return chain;
+    } else if (a.row16) {
+        // compact row: three weights and three 10-bit accumulator indices; byte offset of an accumulator's low limb =
+        // 8 idx (+ 4 when idx & 16: the limbs swap places every 16 accumulators, see tie_slot_w)
+        (void)dummy;
+        const uint32_t pk = row.a.w;
+        const bool chain = (pk >> 31) != 0u;
+        const uint32_t i0 = pk & 1023u, i1 = (pk >> 10) & 1023u, i2 = (pk >> 20) & 1023u;
+        tie_slot_w(acc_s, row.a.x, (i0 << 3) + ((i0 & 16u) >> 2), m, a.L, maskL);
+        tie_slot_w(acc_s, row.a.y, (i1 << 3) + ((i1 & 16u) >> 2), m, a.L, maskL);
+        tie_slot_w(acc_s, row.a.z, (i2 << 3) + ((i2 & 16u) >> 2), m, a.L, maskL);
+        start = 0u;
+        cnt = 0u;
+        if (chain) {
+            const uint2 ci = __ldg(a.xinfo + row.b.x);
+            start = ci.x;
+            cnt = ci.y;
+        }
         return chain;
     } else {
         const bool chain = (row.b.w >> 31) != 0u;
@@ -416,18 +444,20 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             uint32_t bad = 0u;
             int nvalid = 0;
 #pragma unroll 1
-            for (int it = 0; it < iters; ++it) {
-                const int base = it * (kTieU * kTG) + gtid;
-                uint32_t u[kTieU];
-                unsigned col[kTieU];
+            // (kTieU1 loads of each array in flight per thread: this is the pass that waits for DRAM)
+            const int iters1 = (n + kTieU1 * kTG - 1) / (kTieU1 * kTG);
+            for (int it = 0; it < iters1; ++it) {
+                const int base = it * (kTieU1 * kTG) + gtid;
+                uint32_t u[kTieU1];
+                unsigned col[kTieU1];
 #pragma unroll
-                for (int k = 0; k < kTieU; ++k) {
+                for (int k = 0; k < kTieU1; ++k) {
                     const bool in = base + k * kTG < n;
                     u[k] = in ? VT::bits(vals, base + k * kTG, a.lut) : 0u;
                     col[k] = in ? (unsigned)__ldg(cols + base + k * kTG) : 0u;
                 }
 #pragma unroll
-                for (int k = 0; k < kTieU; ++k) {
+                for (int k = 0; k < kTieU1; ++k) {
                     const bool nz = (u[k] << 1) != 0u;                     // +0.0 / -0.0 are not entries
                     const bool valid = nz && col[k] < (unsigned)n_genes;
                     bad |= (nz && u[k] > 0x7F800000u) ? 1u : 0u;           // negative or NaN: not for this kernel
@@ -496,6 +526,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             }
         }
 
+        if (a.skip & 4) continue;                          // (timing experiments only: stop after P2)
         // ---------------- P3: entries into position order; class counts per chunk; the tail list ------------------
         const int ch = max(1, (npos + kTG - 1) / kTG);     // items per chunk (thread) in P6
         const uint32_t magic = ((1u << 20) + (uint32_t)ch - 1u) / (uint32_t)ch;
@@ -555,6 +586,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
             continue;
         }
 
+        if (a.skip & 8) continue;                          // (timing experiments only: stop after P3)
         // ---------------- P5: exclusive scan of the counters in (class, chunk) order ------------------------------
         {
             // thread t scans the kTieD counters [kTieD t, kTieD t + kTieD) of class kTieD t / kTG
@@ -586,6 +618,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         }
         group_bar(barid);
 
+        if (a.skip & 16) continue;                         // (timing experiments only: stop after P5)
         // the next cell's stored entries on their way from DRAM to L2 while this cell scatters: its first pass (P1) then
         // waits for L2, not for DRAM (one 128-byte line per thread and array)
         if (a.prefetch) {
@@ -637,7 +670,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
 #pragma unroll
                 for (int k = 0; k < kTieP6R; ++k) {
                     cnt[cs[k] * kTG + gtid] = (uint32_t)(rr[k] + 1);      // (in order: the last of a class wins)
-                    mm[k] = (cs[k] != 0u && rr[k] < cutoff) ? (uint32_t)(cutoff - rr[k]) : 0u;
+                    mm[k] = (cs[k] != 0u && rr[k] < cutoff && !(a.skip & 1)) ? (uint32_t)(cutoff - rr[k]) : 0u;
                 }
 #pragma unroll
                 for (int h = 0; h < kTieP6R; h += kTieP6) {
@@ -726,6 +759,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         // record) do not depend on the accumulators: they are loaded before the barrier.  Same number of passes for
         // every thread, and the warp is reconverged first (P7 / P8 leave it split).
         __syncwarp();
+        if (a.skip & 2) { group_bar(barid); continue; }
         double* const orow = a.out_auc + cell * (int64_t)R;
         const int passes9 = (R + kTG - 1) / kTG;
         int r9 = gtid;
