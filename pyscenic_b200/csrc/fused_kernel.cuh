@@ -370,7 +370,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
     // upper bound of the explicit entries: the row length.  Short rows are sorted in shared memory (the storage of
     // the fast path's histograms and bucket arrays), long ones in global scratch.
     int64_t bound = a.n_genes;
-    if (IN != IN_DENSE) bound = a.indptr[cell + 1] - a.indptr[cell];
+    if (IN != IN_DENSE) bound = tmin<int64_t>(tmax<int64_t>(a.indptr[cell + 1] - a.indptr[cell], 0), (int64_t)a.n_genes);
     KeyT* lk;
     PosT* lp;
     if (bound <= a.gen_cap) {
@@ -391,7 +391,7 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
         vals = a.dense + cell * a.row_stride;
     } else {
         const int64_t begin = a.indptr[cell];
-        count = a.indptr[cell + 1] - begin;
+        count = bound;                         // (clamped: a malformed row must not overrun the scratch)
         vals = a.data + begin;
         cols = reinterpret_cast<const IdxT*>(a.indices) + begin;
     }
@@ -400,6 +400,9 @@ __device__ void general_cell(const FusedArgs<ValT>& a, int64_t cell, uint32_t* s
         const bool in = i < count;
         KeyT key = KT::KEY_ZERO;
         if (in) key = KT::make(vals[i]);
+        if (IN != IN_DENSE) {                  // a column index out of range: memory-safe, the entry is dropped
+            if (in && (unsigned)cols[i] >= (unsigned)a.n_genes) key = KT::KEY_ZERO;
+        }
         const bool pred = in && key != KT::KEY_ZERO;
         const unsigned mk = __ballot_sync(0xffffffffu, pred);
         const unsigned mgt = __ballot_sync(0xffffffffu, pred && key < KT::KEY_ZERO);
@@ -525,6 +528,7 @@ struct RowView {
     const ValT* vals;
     const IdxT* cols;        // nullptr for dense rows (column == index)
     int count;               // stored entries (CSR) or n_genes (dense)
+    int n_genes;             // CSR: a stored column index outside [0, n_genes) is treated like an explicit zero
 };
 
 // Visit every element of a row with all threads in lock step (uniform trip count, so `f` may use warp votes):
@@ -542,6 +546,10 @@ __device__ __forceinline__ void stream_row(const RowView<ValT, IdxT>& row, F f) 
             if (i < row.count) {
                 key = KT::make(row.vals[i]);
                 col = (int)row.cols[i];
+                if ((unsigned)col >= (unsigned)row.n_genes) {      // malformed input: memory-safe, the entry is dropped
+                    key = KT::KEY_ZERO;
+                    col = 0;
+                }
             }
             f(key != KT::KEY_ZERO, key, col);
         }
@@ -680,12 +688,15 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
             const int64_t begin = a.indptr[cell];
             row.vals = a.data + begin;
             row.cols = reinterpret_cast<const IdxT*>(a.indices) + begin;
-            row.count = (int)(a.indptr[cell + 1] - begin);
+            // (a canonical row holds at most n_genes entries; a longer one -- duplicates -- must not overrun the scratch
+            // of the general path, a negative length must not be walked at all)
+            row.count = (int)tmin<int64_t>(tmax<int64_t>(a.indptr[cell + 1] - begin, 0), (int64_t)n_genes);
         } else {
             row.vals = a.dense + cell * a.row_stride;
             row.cols = nullptr;
             row.count = n_genes;
         }
+        row.n_genes = n_genes;
 
         // ---------------- LOAD ---------------------------------------------------------------------------------
         // direct mode: every explicit entry of the cell sits in registers (kItems per thread).
@@ -710,7 +721,11 @@ __global__ void __launch_bounds__(kF, 2) aucell_fused_kernel(const FusedArgs<Val
                 for_slots<kItems>(nk, [&](auto K) {
                     constexpr int k = decltype(K)::value;
                     const int i = k * kF + tid;
-                    if (i < row.count) { v[k] = row.vals[i]; c[k] = (int)row.cols[i]; }
+                    if (i < row.count) {
+                        v[k] = row.vals[i];
+                        c[k] = (int)row.cols[i];
+                        if ((unsigned)c[k] >= (unsigned)n_genes) { v[k] = (ValT)0; c[k] = 0; }      // malformed input: dropped
+                    }
                 });
                 for_slots<kItems>(nk, [&](auto K) {
                     constexpr int k = decltype(K)::value;

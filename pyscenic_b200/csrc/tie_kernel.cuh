@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
                     const bool nz = (u[k] << 1) != 0u;                     // +0.0 / -0.0 are not entries
                     const bool valid = nz && col[k] < (unsigned)n_genes;
                     bad |= (nz && u[k] > 0x7F800000u) ? 1u : 0u;           // negative or NaN: not for this kernel
-                    nvalid += valid ? 1 : 0;
+                    nvalid += nz ? 1 : 0;                                  // (an invalid column leaves the bit count short: P2 hands the cell over)
                     const unsigned pos = ip[valid ? col[k] : 0u];
                     rep[valid ? bin_of(u[k]) : (uint32_t)kTieNB] = u[k];
                     atomicOr(&A[valid ? (pos >> 5) : (unsigned)dummy_word], valid ? (1u << (pos & 31)) : 0u);

@@ -999,3 +999,35 @@ def test_dense_host_call_squeezes_zeros_out_on_the_host(unweighted, monkeypatch)
         out = np.full((n_cells, len(reg[0])), -1.0)
         _native.check(lib.aucell_dense_f32_host(plan._handle, Xd.ctypes.data, n_cells, n_genes, out.ctypes.data, None, 0))
         assert np.array_equal(out, want_d)
+
+
+@pytest.mark.gpu
+def test_malformed_device_csr_is_memory_safe():
+    """Device-side CSR input is not validated by a separate pass (the Python wrapper checks scipy input on the host):
+    a column index outside [0, n_genes) must not be used as an address -- the tie-class kernels hand such a cell over
+    (the bit count does not match) and the general kernel drops the entry, i.e. ranks the cell as if it were zero."""
+    import scipy.sparse as sp
+    import torch
+
+    n_cells, n_genes = 600, 5003
+    rs = np.random.RandomState(17)
+    X = synth.dense_counts(rs, n_cells, n_genes, 0.08)
+    m = sp.csr_matrix(X)
+    reg = synth.make_regulons(rs, n_genes, 60, 10, 300, weighted=True)
+    cutoff = O.derive_rank_cutoff(0.05, n_genes)
+    perm = np.random.RandomState(3).permutation(n_genes)
+    bad_idx = m.indices.astype(np.int32).copy()
+    fixed = X.copy()
+    for r, col in ((5, n_genes), (77, n_genes + 12345), (300, 2_000_000_000), (451, -7)):
+        e = m.indptr[r] + 3
+        fixed[r, m.indices[e]] = 0.0                      # the entry the kernels must ignore
+        bad_idx[e] = col
+    good = sp.csr_matrix(fixed)
+    with _plan_for(n_genes, perm, reg, cutoff) as plan:
+        got = plan.aucell_csr(cuda(m.indptr.astype(np.int64)), cuda(bad_idx), cuda(m.data)).cpu().numpy()
+        want = plan.aucell_csr(cuda(good.indptr.astype(np.int64)), cuda(good.indices.astype(np.int32)), cuda(good.data)).cpu().numpy()
+        fs = plan.fast_stats()
+        plan.set_fast_path(False)
+        got_general = plan.aucell_csr(cuda(m.indptr.astype(np.int64)), cuda(bad_idx), cuda(m.data)).cpu().numpy()
+    assert fs["handed_duplicate_column"] >= 4
+    assert np.array_equal(got, want) and np.array_equal(got_general, want)
