@@ -121,3 +121,44 @@ def test_gloo_world2_scatter_of_one_matrix_and_gather(tmp_path):
     out = str(tmp_path / "result.txt")
     mp.spawn(_scatter_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def _shared_result_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+
+    from pyscenic_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_cells, n_reg = 103, 5
+    bounds = sharding.shard_bounds(n_cells, world)
+    c0, c1 = bounds[rank]
+    full = sharding._shared_result(n_cells, n_reg, (c0, c1), None, 0)
+    assert full.shape == (n_cells, n_reg)
+    want = np.random.RandomState(5).rand(n_cells, n_reg)             # same on every rank
+    full[c0:c1] = want[c0:c1]                                        # every rank writes its own cell range
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        ok = np.array_equal(np.asarray(full), want)                  # rank 0 sees what the others wrote
+    again = sharding._shared_result(n_cells, n_reg, (c0, c1), None, 0)
+    ok = ok and again is full                                        # kept between calls of the same shape
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        leftovers = [f for f in os.listdir("/dev/shm") if f.startswith("aucell_b200_%d_" % os.getpid())]
+        open(out_path, "w").write("ok" if int(flag) == 1 and not leftovers else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not os.path.isdir("/dev/shm"), reason="needs /dev/shm")
+def test_gloo_world2_result_in_shared_host_memory(tmp_path):
+    """The result buffer of the one-box multi-GPU job (sharding._shared_result): created by rank 0 under /dev/shm, mapped
+    by every rank, written in cell ranges, read by rank 0; unlinked at once, kept between calls."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_shared_result_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
