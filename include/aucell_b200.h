@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host, aucell_cast_f64_to_f32; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -158,6 +158,11 @@ int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_
  * not have), or when the plan has no tie-class kernel: the caller then uses aucell_dense_f32_host / device chunks. */
 int aucell_dense_strided_host(const aucell_plan_t* plan, const void* h_expr, int is_f64, int64_t n_cells,
                               int64_t cell_stride, int64_t gene_stride, double* h_out_auc, int32_t* h_out_nnz);
+/* float64 -> float32 on all host cores, with the check the ranking needs: returns 1 when every value survives the cast
+ * unchanged (NaN counts as unchanged), 0 when one does not (a cast that changes values may create ties the input does
+ * not have: the caller then keeps float64 and uses the *_f64 entry points), negative on bad arguments.  numpy needs
+ * three single-threaded passes for the same answer (seconds on a few hundred million stored values). */
+int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n);
 /* The host-buffer calls keep their staging (four chunk slots per device: a stream, a device buffer, page-locked host
  * buffers -- a few hundred MB) for the life of the process, because a plan is made per aucell() call and page-locking
  * costs more than ranking 300,000 cells.  This frees it (device < 0: on every device). */

@@ -76,10 +76,12 @@ def _dense_values(values: np.ndarray) -> np.ndarray:
         # int64 beyond 2^53 is not representable; the reference would rank the integers themselves
         if np.abs(v).max() > (1 << 53):
             raise ValueError("integer expression values beyond 2^53 are not supported")
-    v32 = v64.astype(np.float32)
-    if np.array_equal(v32.astype(np.float64), v64, equal_nan=True):
-        return v32
-    return v64
+    # cast + exactness check on all host cores (numpy: three single-threaded passes)
+    v32 = np.empty(v64.shape, dtype=np.float32)
+    exact = _native.load().aucell_cast_f64_to_f32(v64.ctypes.data, v32.ctypes.data, v64.size)
+    if exact < 0:
+        _native.check(exact)
+    return v32 if exact == 1 else v64
 
 
 def _torch_device(device: int):

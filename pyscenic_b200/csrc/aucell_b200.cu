@@ -1553,6 +1553,31 @@ int aucell_dense_strided_host(const aucell_plan_t* p, const void* h_expr, int is
     return rc == kNotCompacted ? AUCELL_NOT_SPARSE : rc;
 }
 
+int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n) {
+    if (n < 0 || (n > 0 && (!h_src || !h_dst))) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    const int threads = n < ((int64_t)1 << 20) ? 1 : host_threads();
+    std::vector<int> bad((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t b = n * t / threads, e = n * (t + 1) / threads;
+        int inexact = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const double v = h_src[i];
+            const float f = (float)v;
+            h_dst[i] = f;
+            inexact |= ((double)f == v || v != v) ? 0 : 1;      // (NaN stays NaN)
+        }
+        bad[(size_t)t] = inexact;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        try { pool.emplace_back(work, t); } catch (...) { work(t); }
+    }
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int b : bad) if (b) return 0;
+    return 1;
+}
+
 int aucell_b200_release_staging(int device) {
     std::vector<DeviceStaging*> which;
     {
