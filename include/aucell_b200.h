@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host, aucell_cast_f64_to_f32; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host, aucell_cast_f64_to_f32, aucell_cast_i64_to_i32; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -163,6 +163,9 @@ int aucell_dense_strided_host(const aucell_plan_t* plan, const void* h_expr, int
  * not have: the caller then keeps float64 and uses the *_f64 entry points), negative on bad arguments.  numpy needs
  * three single-threaded passes for the same answer (seconds on a few hundred million stored values). */
 int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n);
+/* int64 -> int32 column indices on all host cores (scipy switches to int64 indices beyond 2^31 stored entries: the
+ * 1.3 M-cell matrix): returns 1 when every value lies in [0, 2^31), 0 when not, negative on bad arguments. */
+int aucell_cast_i64_to_i32(const int64_t* h_src, int32_t* h_dst, int64_t n);
 /* The host-buffer calls keep their staging (four chunk slots per device: a stream, a device buffer, page-locked host
  * buffers -- a few hundred MB) for the life of the process, because a plan is made per aucell() call and page-locking
  * costs more than ranking 300,000 cells.  This frees it (device < 0: on every device). */

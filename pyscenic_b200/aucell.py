@@ -219,12 +219,30 @@ def _csr_auc_shard(plan: AUCellPlan, indptr, indices, data, out: np.ndarray, dev
         out[c0:c1] = plan.aucell_csr(ip, ix, dv).cpu().numpy()
 
 
+def _indices_i32(indices: np.ndarray) -> np.ndarray:
+    """Column indices as int32.  scipy switches to int64 indices beyond 2^31 stored entries (the 1.3 M-cell matrix):
+    narrowed on all host cores by the library (numpy: one single-threaded pass over 20 GB)."""
+    ix = np.asarray(indices)
+    if ix.dtype == np.int32:
+        return np.ascontiguousarray(ix)
+    if ix.dtype != np.int64:
+        return np.ascontiguousarray(ix, dtype=np.int32)
+    ix = np.ascontiguousarray(ix)
+    out = np.empty(ix.shape, dtype=np.int32)
+    ok = _native.load().aucell_cast_i64_to_i32(ix.ctypes.data, out.ctypes.data, ix.size)
+    if ok < 0:
+        _native.check(ok)
+    if ok == 0:
+        raise ValueError("column indices outside [0, 2^31)")
+    return out
+
+
 def _canonical_csr(mtx):
     import scipy.sparse as sp
 
     csr = mtx if sp.isspmatrix_csr(mtx) else sp.csr_matrix(mtx)
     indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
-    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    indices = _indices_i32(csr.indices)
     # sorted, duplicate-free rows are what the kernels need; the library checks that on all host cores (scipy's own
     # has_canonical_format is a single-threaded scan: 2.5 s for the 1.3 M-cell benchmark matrix)
     ok = _native.load().aucell_csr_is_canonical(indptr.ctypes.data, indices.ctypes.data, csr.shape[0], csr.shape[1])
@@ -234,7 +252,7 @@ def _canonical_csr(mtx):
         csr = csr.copy()
         csr.sum_duplicates()
         indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
-        indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        indices = _indices_i32(csr.indices)
     data = csr.data
     if data.dtype != np.float32:
         d = _dense_values(data)

@@ -1578,6 +1578,30 @@ int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n) {
     return 1;
 }
 
+int aucell_cast_i64_to_i32(const int64_t* h_src, int32_t* h_dst, int64_t n) {
+    if (n < 0 || (n > 0 && (!h_src || !h_dst))) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    const int threads = n < ((int64_t)1 << 20) ? 1 : host_threads();
+    std::vector<int> bad((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t b = n * t / threads, e = n * (t + 1) / threads;
+        uint64_t high = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const int64_t v = h_src[i];
+            h_dst[i] = (int32_t)v;
+            high |= (uint64_t)v >> 31;                           // negative or >= 2^31
+        }
+        bad[(size_t)t] = high != 0 ? 1 : 0;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        try { pool.emplace_back(work, t); } catch (...) { work(t); }
+    }
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int b : bad) if (b) return 0;
+    return 1;
+}
+
 int aucell_b200_release_staging(int device) {
     std::vector<DeviceStaging*> which;
     {

@@ -269,3 +269,31 @@ def test_concurrent_builds_are_serialised_and_decided_by_content(tmp_path, monke
     with open(lib + ".src.sha256", "w") as fh:
         fh.write("0" * 64 + "\n")
     assert _native.is_stale()
+
+
+def test_host_cast_helpers():
+    """aucell_cast_f64_to_f32 / aucell_cast_i64_to_i32 (host threads, no GPU) behind aucell._dense_values / _indices_i32."""
+    from pyscenic_b200.aucell import _dense_values, _indices_i32
+
+    rs = np.random.RandomState(1)
+    counts = np.floor(rs.exponential(3.0, size=3_000_000))
+    v = _dense_values(counts)
+    assert v.dtype == np.float32 and np.array_equal(v.astype(np.float64), counts)
+    special = np.array([1.0, np.nan, np.inf, -np.inf, -0.0, 2.5, 2.0 ** -149])
+    v = _dense_values(special)
+    assert v.dtype == np.float32 and np.array_equal(v.astype(np.float64), special, equal_nan=True)
+    assert np.signbit(v[4])
+    for bad in (0.1, 1e300, 2.0 ** -150, 16777217.0):                  # not float32 values: the matrix stays float64
+        x = counts.copy()
+        x[-1] = bad
+        assert _dense_values(x).dtype == np.float64
+    assert _dense_values(np.arange(7, dtype=np.int64)).dtype == np.float32
+    ix = rs.randint(0, 28000, size=2_000_000).astype(np.int64)
+    got = _indices_i32(ix)
+    assert got.dtype == np.int32 and np.array_equal(got, ix)
+    for bad in (2 ** 31, -1):
+        y = ix.copy()
+        y[123] = bad
+        with pytest.raises(ValueError):
+            _indices_i32(y)
+    assert _indices_i32(np.array([3, 4], dtype=np.int32)).dtype == np.int32
