@@ -149,7 +149,9 @@ int aucell_csr_f32_host(const aucell_plan_t* plan, const int64_t* h_indptr, cons
                         int64_t chunk_cells);
 int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_t n_cells, int64_t row_stride,
                           double* h_out_auc, int32_t* h_out_nnz, int64_t chunk_cells);
-/* A host matrix in dense storage as a pandas DataFrame holds it: float32 (is_f64 = 0) or float64 values, cell-major
+/* (replaces the DataFrame form of pyscenic.aucell.aucell, reference src/pyscenic/aucell.py:185-213 -- `exp_mtx` is
+ * `pd.DataFrame` (n_cells x n_genes) there; this takes `exp_mtx.values` without a transposing or casting copy.)
+ * A host matrix in dense storage as a pandas DataFrame holds it: float32 (is_f64 = 0) or float64 values, cell-major
  * (gene_stride == 1, cell_stride >= n_genes) or gene-major (cell_stride == 1, gene_stride >= n_cells; strides in
  * elements).  Expression matrices are mostly zeros: host threads squeeze them out in one pass at memory speed and the
  * call continues as aucell_csr_f32_host -- a fraction of the bytes over PCIe, and the CSR kernels on the device.
