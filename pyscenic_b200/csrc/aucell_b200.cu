@@ -1051,6 +1051,69 @@ template <> bool compact_row_t<double>(const double* row, int64_t n, int32_t* id
     return ok;
 }
 
+// One tile of a gene-major block: `tn` consecutive cells x G genes; the non-zeros of gene g are appended to their cells'
+// lists (cell i: tix / tvv [i * capR, (i + 1) * capR), length cur[i]).  AVX2: eight float32 / four float64 cells per
+// compare, only the non-zero lanes are visited (93 % of the values are zeros).
+template <typename T>
+inline void tile_put(const T* col, int64_t i, int64_t rs, int64_t g, int64_t capR, int64_t* cur, int32_t* tix, float* tvv,
+                     bool& ok, bool& overflow) {
+    float f;
+    ok &= to_f32_exact(col[i * rs], f);
+    const int64_t k = cur[i];
+    if (k >= capR) { overflow = true; return; }
+    tix[i * capR + k] = (int32_t)g;
+    tvv[i * capR + k] = f;
+    cur[i] = k + 1;
+}
+template <typename T>
+void scan_tile_scalar(const T* tile, int64_t rs, int64_t cs, int64_t tn, int64_t G, int64_t capR, int64_t* cur,
+                      int32_t* tix, float* tvv, bool& ok, bool& overflow) {
+    for (int64_t g = 0; g < G; ++g) {
+        const T* col = tile + g * cs;
+        for (int64_t i = 0; i < tn; ++i)
+            if (!is_zero_bits(col + i * rs)) tile_put<T>(col, i, rs, g, capR, cur, tix, tvv, ok, overflow);
+    }
+}
+#ifdef AUCELL_HAVE_AVX2_PATH
+__attribute__((target("avx2"))) inline unsigned nz_lanes(const float* p) {
+    return (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_loadu_ps(p), _mm256_setzero_ps(), _CMP_NEQ_UQ));
+}
+__attribute__((target("avx2"))) inline unsigned nz_lanes(const double* p) {
+    return (unsigned)_mm256_movemask_pd(_mm256_cmp_pd(_mm256_loadu_pd(p), _mm256_setzero_pd(), _CMP_NEQ_UQ));
+}
+template <typename T>
+__attribute__((target("avx2"))) void scan_tile_avx2(const T* tile, int64_t cs, int64_t tn, int64_t G, int64_t capR,
+                                                    int64_t* cur, int32_t* tix, float* tvv, bool& ok, bool& overflow) {
+    constexpr int64_t V = 32 / (int64_t)sizeof(T);            // cells per 256-bit vector (consecutive: rs == 1)
+    for (int64_t g = 0; g < G; ++g) {
+        const T* col = tile + g * cs;
+        int64_t i = 0;
+        for (; i + V <= tn; i += V) {
+            unsigned m = nz_lanes(col + i);
+            while (m) {
+                const int b = __builtin_ctz(m);
+                m &= m - 1;
+                tile_put<T>(col, i + b, 1, g, capR, cur, tix, tvv, ok, overflow);
+            }
+        }
+        for (; i < tn; ++i)
+            if (!is_zero_bits(col + i)) tile_put<T>(col, i, 1, g, capR, cur, tix, tvv, ok, overflow);
+    }
+}
+#endif
+template <typename T>
+void scan_tile(const T* tile, int64_t rs, int64_t cs, int64_t tn, int64_t G, int64_t capR, int64_t* cur, int32_t* tix,
+               float* tvv, bool& ok, bool& overflow) {
+#ifdef AUCELL_HAVE_AVX2_PATH
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && rs == 1) {
+        scan_tile_avx2<T>(tile, cs, tn, G, capR, cur, tix, tvv, ok, overflow);
+        return;
+    }
+#endif
+    scan_tile_scalar<T>(tile, rs, cs, tn, G, capR, cur, tix, tvv, ok, overflow);
+}
+
 // Rows [c0, c0 + nc) of a strided host matrix (element (r, g) at base[r * rs + g * cs]; cs == 1: cell-major rows,
 // rs == 1: gene-major, the layout of a DataFrame block) -> CSR with float32 values, on `threads` host threads.
 // Returns false when a value is not exact in float32 or the rows turn out far denser than `density`.
@@ -1084,7 +1147,7 @@ bool compact_block(const T* base, int64_t rs, int64_t cs, int64_t c0, int64_t nc
         } else {
             // gene-major: tiles of kTile cells; a gene contributes kTile consecutive values, whose non-zeros are appended
             // to their cells' lists (fixed capacity per cell inside the tile: overflow = far denser than expected)
-            constexpr int kTile = 128;
+            constexpr int kTile = 128;            // (64 .. 512 measured: no clear difference)
             int64_t capR = std::min<int64_t>(G, (int64_t)((double)G * density * 2.0) + 256);
             RawBuf<int32_t> tix;
             RawBuf<float> tvv;
@@ -1096,19 +1159,7 @@ bool compact_block(const T* base, int64_t rs, int64_t cs, int64_t c0, int64_t nc
                 for (;;) {
                     bool overflow = false;
                     for (int64_t i = 0; i < tn; ++i) cur[i] = 0;
-                    for (int64_t g = 0; g < G; ++g) {
-                        const T* col = base + g * cs + (c0 + t0) * rs;      // (rs == 1: tn consecutive values)
-                        for (int64_t i = 0; i < tn; ++i) {
-                            if (is_zero_bits(col + i * rs)) continue;
-                            float f;
-                            ok &= to_f32_exact(col[i * rs], f);
-                            const int64_t k = cur[i];
-                            if (k >= capR) { overflow = true; continue; }
-                            tix.data()[i * capR + k] = (int32_t)g;
-                            tvv.data()[i * capR + k] = f;
-                            cur[i] = k + 1;
-                        }
-                    }
+                    scan_tile<T>(base + (c0 + t0) * rs, rs, cs, tn, G, capR, cur, tix.data(), tvv.data(), ok, overflow);
                     if (!overflow) break;
                     capR = std::min<int64_t>(G, capR * 2);       // a cell far denser than the sample: once more, with room
                     tix.grow((size_t)(kTile * capR), 0);
