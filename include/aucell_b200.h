@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host, aucell_cast_f64_to_f32, aucell_cast_i64_to_i32; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
+#define AUCELL_B200_ABI_VERSION 4   /* 4: + aucell_csr_is_canonical, aucell_b200_release_staging, aucell_dense_strided_host, aucell_cast_f64_to_f32, aucell_cast_i64_to_i32, aucell_host_dense_to_csr; 3: + aucell_plan_set_fast_path, aucell_plan_fast_stats, aucell_csr16_lut8_f32, aucell_csr_lut8_f32, aucell_count_nonzero_csr_f32, aucell_binarize_*; 2: + aucell_csr16_f32, aucell_rss_f64, aucell_plan_last_host_bytes */
 
 enum {
     AUCELL_OK = 0,
@@ -160,6 +160,14 @@ int aucell_dense_f32_host(const aucell_plan_t* plan, const float* h_expr, int64_
  * not have), or when the plan has no tie-class kernel: the caller then uses aucell_dense_f32_host / device chunks. */
 int aucell_dense_strided_host(const aucell_plan_t* plan, const void* h_expr, int is_f64, int64_t n_cells,
                               int64_t cell_stride, int64_t gene_stride, double* h_out_auc, int32_t* h_out_nnz);
+/* The host-side half of aucell_dense_strided_host on its own (no GPU): a dense host matrix (float32 / float64,
+ * cell-major or gene-major, strides in elements) -> CSR with float32 values and sorted int32 columns, zeros (+0.0 / -0.0)
+ * dropped, NaN kept; one pass on all host cores.  h_indptr [n_cells + 1] and *out_nnz are always filled; h_indices /
+ * h_values hold `capacity` entries (AUCELL_ERR_NOMEM when that is fewer than *out_nnz: call again with larger arrays).
+ * Returns AUCELL_NOT_SPARSE (1), nothing else written, when a float64 value does not survive the cast to float32. */
+int aucell_host_dense_to_csr(const void* h_expr, int is_f64, int64_t n_cells, int64_t n_genes, int64_t cell_stride,
+                             int64_t gene_stride, int64_t* h_indptr, int32_t* h_indices, float* h_values, int64_t capacity,
+                             int64_t* out_nnz);
 /* float64 -> float32 on all host cores, with the check the ranking needs: returns 1 when every value survives the cast
  * unchanged (NaN counts as unchanged), 0 when one does not (a cast that changes values may create ties the input does
  * not have: the caller then keeps float64 and uses the *_f64 entry points), negative on bad arguments.  numpy needs

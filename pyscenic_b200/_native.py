@@ -60,6 +60,7 @@ EXPORTED_SYMBOLS = [
     "aucell_dense_strided_host",
     "aucell_cast_f64_to_f32",
     "aucell_cast_i64_to_i32",
+    "aucell_host_dense_to_csr",
     "aucell_b200_launch_count",
     "aucell_plan_path_stats",
     "aucell_plan_last_host_bytes",
@@ -265,6 +266,8 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
         lib.aucell_cast_f64_to_f32.restype = c_int
         lib.aucell_cast_i64_to_i32.argtypes = [p, p, i64]
         lib.aucell_cast_i64_to_i32.restype = c_int
+        lib.aucell_host_dense_to_csr.argtypes = [p, c_int, i64, i64, i64, i64, p, p, p, i64, p]
+        lib.aucell_host_dense_to_csr.restype = c_int
         lib.aucell_b200_release_staging.argtypes = [c_int]
         lib.aucell_b200_release_staging.restype = c_int
         lib.aucell_dense_f32_host.argtypes = [p, p, i64, i64, p, p, i64]

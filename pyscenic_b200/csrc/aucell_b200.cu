@@ -1604,6 +1604,49 @@ int aucell_dense_strided_host(const aucell_plan_t* p, const void* h_expr, int is
     return rc == kNotCompacted ? AUCELL_NOT_SPARSE : rc;
 }
 
+int aucell_host_dense_to_csr(const void* h_expr, int is_f64, int64_t n_cells, int64_t n_genes, int64_t cell_stride,
+                             int64_t gene_stride, int64_t* h_indptr, int32_t* h_indices, float* h_values, int64_t capacity,
+                             int64_t* out_nnz) {
+    if (n_cells < 0 || n_genes < 1 || n_genes > INT32_MAX) return fail(AUCELL_ERR_INVALID, "bad n_cells / n_genes");
+    if (!h_indptr || !out_nnz || (n_cells > 0 && !h_expr)) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    const bool cell_major = gene_stride == 1 && cell_stride >= n_genes;
+    const bool gene_major = cell_stride == 1 && gene_stride >= n_cells;
+    if (!cell_major && !gene_major) return fail(AUCELL_ERR_INVALID, "one of the two strides must be 1 and the other span the matrix");
+    *out_nnz = 0;
+    h_indptr[0] = 0;
+    if (n_cells == 0) return AUCELL_OK;
+    const int threads = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), n_cells));
+    // density of a sample: 64 evenly spaced cells x up to 4096 evenly spaced genes (only sizes the first buffers)
+    const int64_t pc = std::min<int64_t>(n_cells, 64), pg = std::min<int64_t>(n_genes, 4096);
+    int64_t nz = 0;
+    for (int64_t a = 0; a < pc; ++a)
+        for (int64_t b = 0; b < pg; ++b) {
+            const int64_t off = (n_cells * a / pc) * cell_stride + (n_genes * b / pg) * gene_stride;
+            nz += (is_f64 ? is_zero_bits(static_cast<const double*>(h_expr) + off) : is_zero_bits(static_cast<const float*>(h_expr) + off)) ? 0 : 1;
+        }
+    const double density = (double)nz / (double)(pc * pg);
+    std::vector<RawBuf<int32_t>> t_idx((size_t)threads);
+    std::vector<RawBuf<float>> t_val((size_t)threads);
+    std::vector<int64_t> indptr;
+    RawBuf<int32_t> indices;
+    RawBuf<float> values;
+    const bool ok = is_f64 ? compact_block<double>(static_cast<const double*>(h_expr), cell_stride, gene_stride, 0, n_cells, n_genes,
+                                                   threads, density, t_idx, t_val, indptr, indices, values)
+                           : compact_block<float>(static_cast<const float*>(h_expr), cell_stride, gene_stride, 0, n_cells, n_genes,
+                                                  threads, density, t_idx, t_val, indptr, indices, values);
+    if (!ok) return AUCELL_NOT_SPARSE;
+    const int64_t nnz = indptr[(size_t)n_cells];
+    *out_nnz = nnz;
+    memcpy(h_indptr, indptr.data(), sizeof(int64_t) * (size_t)(n_cells + 1));
+    if (nnz > capacity) return fail(AUCELL_ERR_NOMEM, "capacity of the output arrays is smaller than the number of non-zero values");
+    if (nnz > 0 && (!h_indices || !h_values)) return fail(AUCELL_ERR_INVALID, "NULL pointer");
+    if (nnz > 0) {
+        memcpy(h_indices, indices.data(), sizeof(int32_t) * (size_t)nnz);
+        memcpy(h_values, values.data(), sizeof(float) * (size_t)nnz);
+    }
+    return AUCELL_OK;
+}
+
 int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n) {
     if (n < 0 || (n > 0 && (!h_src || !h_dst))) return fail(AUCELL_ERR_INVALID, "NULL pointer");
     const int threads = n < ((int64_t)1 << 20) ? 1 : host_threads();

@@ -297,3 +297,80 @@ def test_host_cast_helpers():
         with pytest.raises(ValueError):
             _indices_i32(y)
     assert _indices_i32(np.array([3, 4], dtype=np.int32)).dtype == np.int32
+
+
+def _host_dense_to_csr(arr, n_cells=None, n_genes=None):
+    """aucell_host_dense_to_csr on a 2-D numpy array in either layout; returns (rc, indptr, indices, values)."""
+    import ctypes
+
+    lib = _native.load()
+    es = arr.dtype.itemsize
+    nc, ng = arr.shape if n_cells is None else (n_cells, n_genes)
+    s0, s1 = arr.strides[0] // es, arr.strides[1] // es
+    indptr = np.full(nc + 1, -1, dtype=np.int64)
+    cap = max(1, nc * ng)
+    indices = np.full(cap, -1, dtype=np.int32)
+    values = np.full(cap, -1.0, dtype=np.float32)
+    nnz = ctypes.c_int64(-1)
+    rc = lib.aucell_host_dense_to_csr(arr.ctypes.data, 1 if arr.dtype == np.float64 else 0, nc, ng, s0, s1,
+                                      indptr.ctypes.data, indices.ctypes.data, values.ctypes.data, cap, ctypes.byref(nnz))
+    return rc, indptr, indices[: max(nnz.value, 0)], values[: max(nnz.value, 0)], nnz.value
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_host_dense_to_csr_equals_scipy(dtype, order):
+    """The squeeze behind aucell_dense_strided_host (host threads, AVX2; no GPU) against scipy, for the layouts and float
+    types a DataFrame block comes in: ragged tile and vector tails, -0.0 / NaN / inf, an all-zero cell, one cell far denser
+    than the rest (the per-cell capacity of a gene-major tile has to grow), padded strides."""
+    import scipy.sparse as sp
+
+    rs = np.random.RandomState(2)
+    n_cells, n_genes = 1337, 2051
+    X = np.where(rs.random_sample((n_cells, n_genes)) < 0.07, np.floor(1 + rs.exponential(2.0, (n_cells, n_genes))), 0.0)
+    X[3] = 0.0
+    X[5, :] = np.arange(1, n_genes + 1) % 7 + 1.0                  # a dense cell among sparse ones
+    X[7, 11] = np.nan
+    X[8, 12] = np.inf
+    X[9, rs.choice(n_genes, 50, replace=False)] = -0.0
+    X[10, -3:] = 2.0
+    X[-1, -1] = 5.0
+    pad = np.full((n_cells + 5, n_genes + 3), 9.0)                 # (strides larger than the matrix)
+    pad[:n_cells, :n_genes] = X
+    big = np.asarray(pad, dtype=dtype, order=order)
+    arr = big[:n_cells, :n_genes]
+    rc, indptr, indices, values, nnz = _host_dense_to_csr(arr)
+    assert rc == 0
+    want = sp.csr_matrix(np.where(np.isnan(X), 1.0, X))           # (the pattern; NaN is a stored value)
+    want.sort_indices()
+    assert nnz == want.nnz and np.array_equal(indptr, want.indptr) and np.array_equal(indices, want.indices)
+    got_vals = np.asarray(X[np.repeat(np.arange(n_cells), np.diff(want.indptr)), want.indices], dtype=np.float32)
+    assert np.array_equal(values, got_vals, equal_nan=True)
+    assert not np.any(values == 0.0)                               # +0.0 / -0.0 are dropped
+
+
+def test_host_dense_to_csr_declines_and_errors():
+    rs = np.random.RandomState(4)
+    X = np.where(rs.random_sample((300, 500)) < 0.1, 1.0, 0.0)
+    for order in ("C", "F"):
+        inexact = np.asarray(X, dtype=np.float64, order=order).copy(order=order)
+        inexact[17, 33] = 0.1
+        rc = _host_dense_to_csr(inexact)[0]
+        assert rc == 1                                             # AUCELL_NOT_SPARSE: keep float64
+    lib = _native.load()
+    import ctypes
+
+    a = np.asarray(X, dtype=np.float32)
+    indptr = np.zeros(301, dtype=np.int64)
+    nnz = ctypes.c_int64(0)
+    small = np.zeros(3, dtype=np.int32)
+    smallv = np.zeros(3, dtype=np.float32)
+    rc = lib.aucell_host_dense_to_csr(a.ctypes.data, 0, 300, 500, 500, 1, indptr.ctypes.data, small.ctypes.data,
+                                      smallv.ctypes.data, 3, ctypes.byref(nnz))
+    assert rc == -5 and nnz.value == int(np.count_nonzero(X)) and indptr[-1] == nnz.value      # AUCELL_ERR_NOMEM, sizes known
+    rc = lib.aucell_host_dense_to_csr(a.ctypes.data, 0, 300, 500, 7, 3, indptr.ctypes.data, small.ctypes.data,
+                                      smallv.ctypes.data, 3, ctypes.byref(nnz))
+    assert rc == -1                                                # neither stride is 1
+    ip = np.full(1, -1, dtype=np.int64)
+    rc = lib.aucell_host_dense_to_csr(a.ctypes.data, 0, 0, 10, 10, 1, ip.ctypes.data, None, None, 0, ctypes.byref(nnz))
+    assert rc == 0 and nnz.value == 0 and ip[0] == 0              # no cells
