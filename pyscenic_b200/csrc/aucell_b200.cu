@@ -1085,8 +1085,14 @@ template <typename T>
 __attribute__((target("avx2"))) void scan_tile_avx2(const T* tile, int64_t cs, int64_t tn, int64_t G, int64_t capR,
                                                     int64_t* cur, int32_t* tix, float* tvv, bool& ok, bool& overflow) {
     constexpr int64_t V = 32 / (int64_t)sizeof(T);            // cells per 256-bit vector (consecutive: rs == 1)
+    constexpr int64_t kAhead = 12;                           // genes: their cache lines are a whole column apart, which
+    const int64_t lines = (tn * (int64_t)sizeof(T) + 63) / 64;   // no hardware prefetcher follows
     for (int64_t g = 0; g < G; ++g) {
         const T* col = tile + g * cs;
+        if (g + kAhead < G) {
+            const char* nxt = reinterpret_cast<const char*>(tile + (g + kAhead) * cs);
+            for (int64_t l = 0; l < lines; ++l) _mm_prefetch(nxt + 64 * l, _MM_HINT_T0);
+        }
         int64_t i = 0;
         for (; i + V <= tn; i += V) {
             unsigned m = nz_lanes(col + i);
