@@ -4,6 +4,8 @@
 #include "launch.cuh"
 
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <thread>
 #if defined(__x86_64__) && defined(__GNUC__)
@@ -611,6 +613,78 @@ namespace {
 
 constexpr int kHostSlots = 4;
 
+// ---- host worker threads --------------------------------------------------------------------------------------------
+// The host-side passes (narrowing, byte-coding, staging copies, squeezing) are short: a chunk's pass takes 1-3 ms, and
+// creating sixteen std::threads for it ~0.3 ms.  The workers are therefore created once and kept (detached, for the
+// life of the process); parallel_tasks(n, f) runs f(0) .. f(n - 1), task 0 on the caller, one parallel region at a time
+// (regions of different callers queue: they would share the cores anyway).  f must not call parallel_tasks itself.
+extern "C++" {
+class HostPool {
+    std::mutex client_mu_;                    // one region at a time
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    int n_workers_ = 0;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_tasks_ = 0, next_ = 0, done_ = 0;
+    void worker() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_work_.wait(lk, [this]() { return fn_ != nullptr && next_ < n_tasks_; });
+            const int t = next_++;
+            const std::function<void(int)>* f = fn_;
+            lk.unlock();
+            (*f)(t);
+            lk.lock();
+            if (++done_ == n_tasks_) cv_done_.notify_all();
+        }
+    }
+public:
+    void run(int n, const std::function<void(int)>& f) {
+        if (n <= 1) {
+            if (n == 1) f(0);
+            return;
+        }
+        std::lock_guard<std::mutex> client(client_mu_);
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            while (n_workers_ < n - 1 && n_workers_ < 63) {
+                try {
+                    std::thread([this]() { worker(); }).detach();
+                    ++n_workers_;
+                } catch (...) {
+                    break;                    // no more threads to be had (container limits): the caller takes what is left
+                }
+            }
+            fn_ = &f;
+            n_tasks_ = n;
+            next_ = 1;                        // task 0 runs on the caller
+            done_ = 0;
+        }
+        cv_work_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        ++done_;
+        while (next_ < n_tasks_) {            // help out (also covers "fewer workers than tasks")
+            const int t = next_++;
+            lk.unlock();
+            f(t);
+            lk.lock();
+            ++done_;
+        }
+        cv_done_.wait(lk, [this]() { return done_ == n_tasks_; });
+        fn_ = nullptr;
+    }
+};
+inline HostPool& host_pool() {
+    static HostPool* pool = new HostPool();   // (never destroyed: its workers outlive main)
+    return *pool;
+}
+template <typename F> inline void parallel_tasks(int n, F&& f) {
+    const std::function<void(int)> fn(std::forward<F>(f));
+    host_pool().run(n, fn);
+}
+}  // extern "C++"
+
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Staging of the host-buffer calls: kHostSlots chunk slots (stream, device buffer, pinned host buffers) PER DEVICE,
@@ -733,19 +807,11 @@ uint32_t narrow_span(const int32_t* src, uint16_t* dst, int64_t n) {
 bool narrow_indices(const int32_t* src, uint16_t* dst, int64_t n, int threads) {
     if (threads <= 1 || n < (1 << 18)) return narrow_span(src, dst, n) == 0;
     std::vector<uint32_t> bad((size_t)threads, 0u);
-    std::vector<std::thread> pool;
-    pool.reserve((size_t)threads - 1);
     const int64_t per = ((n + threads - 1) / threads + 63) & ~int64_t(63);
-    for (int t = 1; t < threads; ++t) {
+    parallel_tasks(threads, [&bad, src, dst, n, per](int t) {
         const int64_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
-        try {
-            pool.emplace_back([&bad, src, dst, t, b, e]() { bad[(size_t)t] = narrow_span(src + b, dst + b, e - b); });
-        } catch (...) {               // no more threads to be had (container limits): do the span here
-            bad[(size_t)t] = narrow_span(src + b, dst + b, e - b);
-        }
-    }
-    bad[0] = narrow_span(src, dst, std::min(n, per));
-    for (auto& th : pool) th.join();
+        bad[(size_t)t] = b < e ? narrow_span(src + b, dst + b, e - b) : 0u;
+    });
     uint32_t any = 0;
     for (uint32_t b : bad) any |= b;
     return any == 0;
@@ -888,13 +954,7 @@ bool encode_values(ValueDict& d, const float* src_f, uint8_t* dst, int64_t n, in
             const int64_t b = pos[(size_t)t], e = end[(size_t)t];
             if (b < e) pos[(size_t)t] = b + encode_span(d, src + b, dst + b, e - b);
         };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; ++t) {
-            if (pos[(size_t)t] >= end[(size_t)t]) continue;
-            try { pool.emplace_back(work, t); } catch (...) { work(t); }
-        }
-        work(0);
-        for (auto& th : pool) th.join();
+        parallel_tasks(threads, work);
         bool done = true;
         for (int t = 0; t < threads; ++t) {
             if (pos[(size_t)t] < end[(size_t)t]) {          // stopped at an unknown value: learn it, go on from there
@@ -925,18 +985,10 @@ void copy_bytes(void* dst, const void* src, size_t n, int threads) {
         return;
     }
     const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) {
-        const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
-        if (b >= e) continue;
-        try {
-            pool.emplace_back([=]() { memcpy((char*)dst + b, (const char*)src + b, e - b); });
-        } catch (...) {
-            memcpy((char*)dst + b, (const char*)src + b, e - b);
-        }
-    }
-    memcpy(dst, src, std::min(n, per));
-    for (auto& th : pool) th.join();
+    parallel_tasks(threads, [=](int t) {
+        const size_t b = std::min(n, per * (size_t)t), e = std::min(n, per * ((size_t)t + 1));
+        if (b < e) memcpy((char*)dst + b, (const char*)src + b, e - b);
+    });
 }
 
 // ---- dense host rows -> CSR on host threads --------------------------------------------------------------------------
@@ -1190,12 +1242,7 @@ bool compact_block(const T* base, int64_t rs, int64_t cs, int64_t c0, int64_t nc
         bad[(size_t)t] = ok ? 0 : 1;
     };
     {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; ++t) {
-            try { pool.emplace_back(work, t); } catch (...) { work(t); }
-        }
-        work(0);
-        for (auto& th : pool) th.join();
+        parallel_tasks(threads, work);
     }
     for (int b : bad) if (b) return false;
     for (int64_t r = 0; r < nc; ++r) indptr[(size_t)r + 1] += indptr[(size_t)r];
@@ -1209,12 +1256,7 @@ bool compact_block(const T* base, int64_t rs, int64_t cs, int64_t c0, int64_t nc
         memcpy(values.data() + e0, t_val[(size_t)t].data(), sizeof(float) * (size_t)(e1 - e0));
     };
     {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; ++t) {
-            try { pool.emplace_back(gather, t); } catch (...) { gather(t); }
-        }
-        gather(0);
-        for (auto& th : pool) th.join();
+        parallel_tasks(threads, gather);
     }
     return true;
 }
@@ -1581,12 +1623,7 @@ int aucell_csr_is_canonical(const int64_t* h_indptr, const int32_t* h_indices, i
         }
         bad[(size_t)t] = b;
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) {
-        try { pool.emplace_back(work, t); } catch (...) { work(t); }
-    }
-    work(0);
-    for (auto& th : pool) th.join();
+    parallel_tasks(threads, work);
     for (int b : bad) if (b) return 0;
     return 1;
 }
@@ -1669,12 +1706,7 @@ int aucell_cast_f64_to_f32(const double* h_src, float* h_dst, int64_t n) {
         }
         bad[(size_t)t] = inexact;
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) {
-        try { pool.emplace_back(work, t); } catch (...) { work(t); }
-    }
-    work(0);
-    for (auto& th : pool) th.join();
+    parallel_tasks(threads, work);
     for (int b : bad) if (b) return 0;
     return 1;
 }
@@ -1693,12 +1725,7 @@ int aucell_cast_i64_to_i32(const int64_t* h_src, int32_t* h_dst, int64_t n) {
         }
         bad[(size_t)t] = high != 0 ? 1 : 0;
     };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) {
-        try { pool.emplace_back(work, t); } catch (...) { work(t); }
-    }
-    work(0);
-    for (auto& th : pool) th.join();
+    parallel_tasks(threads, work);
     for (int b : bad) if (b) return 0;
     return 1;
 }
