@@ -589,30 +589,38 @@ __global__ void __launch_bounds__(kTG* kTieMaxGroups, 1) aucell_tie_kernel(const
         if (a.skip & 8) continue;                          // (timing experiments only: stop after P3)
         // ---------------- P5: exclusive scan of the counters in (class, chunk) order ------------------------------
         {
-            // thread t scans the kTieD counters [kTieD t, kTieD t + kTieD) of class kTieD t / kTG
+            // thread t scans the kTieD counters [kTieD t, kTieD t + kTieD) of class kTieD t / kTG: four 128-bit vectors.
+            // 64 bytes per thread put four lanes of every quarter-warp on the same banks when all lanes touch "their
+            // k-th vector" together (4x the wavefronts, 660 of the cell's 5,500): lane t therefore touches its vectors
+            // in the rotated order (k + t / 2) mod 4, which spreads a quarter-warp over all eight bank groups.
             constexpr int kVec = kTieD / 4;               // 128-bit vectors of counters per thread
-            static_assert(kTieD % 4 == 0 && kTG % kTieD == 0, "counter slices");
+            static_assert(kVec == 4 && kTG % kTieD == 0, "counter slices");
             const int n_cls = min(d_total, kTieD - 1) + 1;
             const bool live = (gtid * kTieD) / kTG < n_cls;
-            uint4 c[kVec];
+            const int rot = (gtid >> 1) & 3;
+            uint4* const mine = reinterpret_cast<uint4*>(cnt) + gtid * kVec;
+            uint32_t q[kVec];                             // q[k]: sum of the vector touched at step k, vector (k + rot) & 3
 #pragma unroll
-            for (int k = 0; k < kVec; ++k) c[k] = live ? reinterpret_cast<const uint4*>(cnt)[gtid * kVec + k] : make_uint4(0u, 0u, 0u, 0u);
-            uint32_t s = 0;
-#pragma unroll
-            for (int k = 0; k < kVec; ++k) s += c[k].x + c[k].y + c[k].z + c[k].w;
+            for (int k = 0; k < kVec; ++k) {
+                const uint4 c = live ? mine[(k + rot) & 3] : make_uint4(0u, 0u, 0u, 0u);
+                q[k] = c.x + c.y + c.z + c.w;
+            }
             uint32_t total;
-            uint32_t run = group_excl_scan(s, misc + kMScanB, lane, gw, barid, total);
+            const uint32_t run0 = group_excl_scan(q[0] + q[1] + q[2] + q[3], misc + kMScanB, lane, gw, barid, total);
             if (live) {
 #pragma unroll
                 for (int k = 0; k < kVec; ++k) {
-                    uint32_t* const wv = reinterpret_cast<uint32_t*>(&c[k]);
+                    const int jk = (k + rot) & 3;         // the vector of this step; what precedes it inside the slice:
+                    uint32_t run = run0;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t v = wv[q];
-                        wv[q] = run;
-                        run += v;
-                    }
-                    reinterpret_cast<uint4*>(cnt)[gtid * kVec + k] = c[k];
+                    for (int k2 = 0; k2 < kVec; ++k2) run += (((k2 + rot) & 3) < jk) ? q[k2] : 0u;
+                    const uint4 c = mine[jk];             // (again: cheaper than sixteen live registers across the scan)
+                    uint4 o;
+                    o.x = run; run += c.x;
+                    o.y = run; run += c.y;
+                    o.z = run; run += c.z;
+                    o.w = run;
+                    mine[jk] = o;
                 }
             }
         }

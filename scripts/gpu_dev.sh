@@ -1,4 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_gpu.log
-timeout 200 python scripts/fuzz_gpu.py 60 43 2>&1 | tail -1
+timeout 300 python scripts/dev_tie.py 200000 2>&1 | grep -E '"fast": 1|kernel 1' | cut -c1-120
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tie_class or byte_coded or config4 or config5" 2>&1 | tail -2
