@@ -374,3 +374,31 @@ def test_host_dense_to_csr_declines_and_errors():
     ip = np.full(1, -1, dtype=np.int64)
     rc = lib.aucell_host_dense_to_csr(a.ctypes.data, 0, 0, 10, 10, 1, ip.ctypes.data, None, None, 0, ctypes.byref(nnz))
     assert rc == 0 and nnz.value == 0 and ip[0] == 0              # no cells
+
+
+def test_host_worker_pool_serves_concurrent_callers():
+    """The persistent host workers (one parallel region at a time, regions of different callers queue): several Python
+    threads call multi-threaded library functions at once, with results checked, and nothing deadlocks."""
+    import threading
+
+    lib = _native.load()
+    rs = np.random.RandomState(3)
+    src = [np.floor(rs.exponential(3.0, size=(1 << 21) + 17 * k)) for k in range(4)]
+    errors = []
+
+    def caller(k):
+        try:
+            for _ in range(6):
+                dst = np.empty(src[k].shape, dtype=np.float32)
+                assert lib.aucell_cast_f64_to_f32(src[k].ctypes.data, dst.ctypes.data, src[k].size) == 1
+                assert np.array_equal(dst.astype(np.float64), src[k])
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=caller, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in threads), "a caller is stuck"
+    assert not errors, errors
